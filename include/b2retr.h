@@ -1,0 +1,206 @@
+/*
+ * b2retr.h — C ABI of libb2retr.so: B200 (sm_100a) Stage-1 retrieval hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its
+ * own: its arithmetic lives in faiss-cpu / torch behind a Python surface.  Every
+ * entry point below names the reference call site whose arithmetic it replaces
+ * (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types cross the ABI.
+ *   - All data pointers are CALLER-OWNED DEVICE pointers unless the name ends in
+ *     `_host`.  The caller keeps them alive until the stream work completes.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  All work is
+ *     enqueued asynchronously on it; nothing synchronises unless stated.
+ *   - Every function returns B2R_OK (0) or a negative B2R_E* code; the message is
+ *     available from b2r_last_error() (thread local).  Nothing throws or exits.
+ *   - The search path never allocates: the caller supplies a workspace of at least
+ *     b2r_index_search_workspace() bytes (256-byte aligned).
+ */
+#ifndef B2RETR_H_
+#define B2RETR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2R_VERSION 100
+
+/* error codes */
+#define B2R_OK 0
+#define B2R_EINVAL (-1)     /* bad argument */
+#define B2R_ECUDA (-2)      /* CUDA runtime / driver error (text in b2r_last_error) */
+#define B2R_ENOMEM (-3)     /* device allocation failed / workspace too small */
+#define B2R_ESTATE (-4)     /* wrong state (e.g. search on an untrained IVF index) */
+#define B2R_EUNSUPPORTED (-5)
+
+/* index kinds — faiss_retrieval.py:46-63 (`_create_index`) */
+#define B2R_KIND_FLAT 0    /* faiss.IndexFlatIP            faiss_retrieval.py:48  */
+#define B2R_KIND_IVF_FLAT 1 /* faiss.IndexIVFFlat(IP)      faiss_retrieval.py:52-55 */
+#define B2R_KIND_IVF_PQ 2  /* faiss.IndexIVFPQ (L2)        faiss_retrieval.py:59-63 */
+
+/* metrics */
+#define B2R_METRIC_IP 0 /* larger is better, results descending */
+#define B2R_METRIC_L2 1 /* squared L2, results ascending (IVFPQ default) */
+
+/* per-query status bits written by b2r_index_search (0 = provably exact) */
+#define B2R_ST_TOO_FEW 1       /* fewer than k candidates passed the threshold */
+#define B2R_ST_NEED_LOWER_TAU 2 /* threshold above (k-th score - 2E): coverage not proven */
+#define B2R_ST_CAND_OVERFLOW 4 /* candidate buffer overflowed */
+#define B2R_ST_RESCORE_OVERFLOW 8 /* rescore window larger than its buffer */
+
+typedef struct b2r_index b2r_index;
+typedef struct b2r_tower b2r_tower;
+
+int b2r_version(void);
+const char* b2r_last_error(void);
+
+/* ------------------------------------------------------------------ index -- */
+
+/* Replaces FAISSIndex._create_index (faiss_retrieval.py:44-81).
+ * d must be a multiple of 64 (TMA/UMMA K-chunk) and <= 256 for the tensor-core
+ * scan.  nlist/pq_m/pq_bits are ignored for B2R_KIND_FLAT. */
+int b2r_index_create(b2r_index** out, int kind, int d, int nlist, int pq_m, int pq_bits,
+                     int metric, int device);
+int b2r_index_destroy(b2r_index* h);
+
+/* Drop all stored vectors (keeps training state). */
+int b2r_index_reset(b2r_index* h);
+
+/* index.ntotal / index.is_trained (read at train.py:231, inference.py:156,
+ * faiss_retrieval.py:90,107,251-252). */
+int64_t b2r_index_ntotal(const b2r_index* h);
+int b2r_index_is_trained(const b2r_index* h);
+
+/* Replaces index.train (faiss_retrieval.py:93): k-means for the coarse
+ * quantiser (+ PQ codebooks).  x: fp32 [n,d] device, un-normalised (the
+ * reference trains before normalising, faiss_retrieval.py:107-108 vs :114-115).
+ * No-op for FLAT.  Synchronises the stream. */
+int b2r_index_train(b2r_index* h, int64_t n, const float* x, uint64_t seed, void* stream);
+
+/* Replaces `faiss.normalize_L2(x); index.add(x)` (faiss_retrieval.py:114-118).
+ * x: fp32 [n,d] device, never modified.  normalize!=0 applies
+ * x *= 1/sqrt(sum x^2) when the sum is > 0 (zero rows stay zero).
+ * Stores an fp32 master row and a bf16 scan row per vector.  May (re)allocate;
+ * synchronises the stream when it does. */
+int b2r_index_add(b2r_index* h, int64_t n, const float* x, int normalize, void* stream);
+
+/* Replaces the python id remap loop `id_map[idx]` (faiss_retrieval.py:159-160):
+ * ids: int64 [ntotal] device copy of id_map (copied into the handle); search then
+ * returns ids[label] (and ids[ntotal-1] for empty slots, the reference's
+ * id_map[-1] wrap-around) instead of labels.  n==0 / ids==NULL clears the map. */
+int b2r_index_set_ids(b2r_index* h, int64_t n, const int64_t* ids, void* stream);
+
+/* Added to every returned label (row-sharded corpora: global = base + local). */
+int b2r_index_set_label_base(b2r_index* h, int64_t base);
+
+/* Tunables (all have defaults): rescore_eps = relative bf16 score error bound
+ * used for the rescore window (default 2^-8 * 1.02 = rigorous for bf16 operands,
+ * fp32 accumulate); cand_factor = target candidates per query as a multiple of k
+ * (default 4); cand_cap = candidate slots per query (default 4096, power of two,
+ * <= 4096). */
+int b2r_index_set_param(b2r_index* h, const char* name, double value);
+double b2r_index_get_param(const b2r_index* h, const char* name);
+
+/* Workspace bytes needed by b2r_index_search for (q, k, nprobe). */
+size_t b2r_index_search_workspace(const b2r_index* h, int q, int k, int nprobe);
+
+/* Replaces `faiss.normalize_L2(q); index.search(q, k)` (faiss_retrieval.py:146-155)
+ * plus the id remap (:159-160).
+ *   queries  fp32 [q,d] device, never modified; normalize as in add.
+ *   D        fp32 [q,k] device: IP descending (L2 ascending for IVF_PQ);
+ *            empty slots hold -3.4028235e38 (IP) / +3.4028235e38 (L2).
+ *   I        int64 [q,k] device: labels (or mapped ids); empty slots -1
+ *            (or ids[ntotal-1] when an id map is set).
+ *   status   int32 [q] device, B2R_ST_* bits per query (0 = provably exact);
+ *            tau_retry fp32 [q] device: threshold to pass back in `tau_in` for a
+ *            retry of the flagged queries.  Both may be NULL.
+ *   tau_in   fp32 [q] device or NULL: caller-provided candidate thresholds
+ *            (skips the sampling pass).
+ * Asynchronous on `stream`. */
+int b2r_index_search(b2r_index* h, int q, const float* queries, int normalize, int k,
+                     int nprobe, float* D, int64_t* I, int32_t* status, float* tau_retry,
+                     const float* tau_in, void* workspace, size_t ws_bytes, void* stream);
+
+/* Share IVF / PQ state with the oracle ("same centroids/codebooks" parity,
+ * SURVEY.md §8c).  Host pointers. centroids fp32 [nlist,d]; codebooks fp32
+ * [pq_m, 2^pq_bits, d/pq_m]. */
+int b2r_index_export_centroids(const b2r_index* h, float* centroids_host);
+int b2r_index_import_centroids(b2r_index* h, const float* centroids_host);
+int b2r_index_export_codebooks(const b2r_index* h, float* codebooks_host);
+int b2r_index_import_codebooks(b2r_index* h, const float* codebooks_host);
+
+/* Inverted-list sizes (int64 [nlist], host) — for oracle cross-checks. */
+int b2r_index_list_sizes(const b2r_index* h, int64_t* sizes_host);
+
+/* Copy stored fp32 master rows [row0,row0+n) to a device buffer (save path,
+ * replaces what faiss.write_index serialises, faiss_retrieval.py:203-206). */
+int b2r_index_get_vectors(const b2r_index* h, int64_t row0, int64_t n, float* out, void* stream);
+
+/* ------------------------------------------------------------ multi-GPU -- */
+
+/* Merge P per-shard results (after the NCCL all-gather).
+ * D_all fp32 [P,q,k], I_all int64 [P,q,k] (each shard's rows best-first, empty
+ * slots I=-1).  largest!=0 for IP.  Writes the global best-first top-k. */
+int b2r_topk_merge(int P, int q, int k, const float* D_all, const int64_t* I_all, float* D_out,
+                   int64_t* I_out, int largest, void* stream);
+
+/* ---------------------------------------------------------------- tower -- */
+
+/* Replaces EmbeddingLayer.forward (two_tower_model.py:42-47): F per-field row
+ * gathers + concat.  tables: device array of F device pointers, table f is fp32
+ * [cards[f], emb_dim]; idx int64 [B,F]; out fp32 [B,ld] with ld >= F*emb_dim,
+ * field f written at columns [f*emb_dim, (f+1)*emb_dim).  Bit-exact copy.
+ * err_flag: int32 device, set to 1 on an out-of-range index (torch raises
+ * IndexError there); may be NULL. */
+int b2r_gather_concat(const float* const* tables, const int64_t* cards, int F, int emb_dim,
+                      const int64_t* idx, int64_t B, float* out, int64_t ld, int32_t* err_flag,
+                      void* stream);
+
+/* BN-folded tower weights (host pointers, row-major [out,in] like nn.Linear).
+ * Folding: W' = W*g/sqrt(var+eps), b' = (b-mean)*g/sqrt(var+eps)+beta
+ * (two_tower_model.py:83-95 in eval mode). */
+typedef struct b2r_tower_weights {
+  int num_fields;           /* F */
+  int emb_dim;              /* 16 */
+  int num_numerical;        /* 13 for UserTower, 0 for AdTower */
+  int hidden1, hidden2, out_dim; /* 512, 256, 256 */
+  const int64_t* cards;     /* [F] host */
+  const float* const* tables; /* [F] DEVICE pointers to fp32 [card,emb_dim] tables */
+  const float* w1; const float* b1; /* [hidden1, F*emb_dim+num_numerical], [hidden1] host */
+  const float* w2; const float* b2; /* [hidden2, hidden1] host */
+  const float* w3; const float* b3; /* [out_dim, hidden2] host */
+} b2r_tower_weights;
+
+/* Replaces UserTower/AdTower construction + load_state_dict + eval(). */
+int b2r_tower_create(b2r_tower** out, const b2r_tower_weights* w, int device);
+int b2r_tower_destroy(b2r_tower* t);
+size_t b2r_tower_workspace(const b2r_tower* t, int64_t B);
+
+/* Replaces UserTower.forward / AdTower.forward (two_tower_model.py:98-121,
+ * :167-184) in eval mode: gather+concat -> 3 GEMMs (bf16 operands, fp32
+ * accumulate) with bias/ReLU -> F.normalize(p=2, eps=1e-12).
+ * cat int64 [B,F]; num fp32 [B,num_numerical] or NULL; out fp32 [B,out_dim]. */
+int b2r_tower_forward(b2r_tower* t, const int64_t* cat, const float* num, int64_t B, float* out,
+                      int32_t* err_flag, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- debug -- */
+/* Test-only helpers (never on the product path). */
+
+/* Full bf16-operand / fp32-accumulate score matrix through the SAME tcgen05
+ * scan kernel in dump mode: out fp32 [q, ntotal]. */
+int b2r_debug_scores_tc(b2r_index* h, int q, const float* queries, int normalize, float* out,
+                        void* workspace, size_t ws_bytes, void* stream);
+/* The same matrix from a plain CUDA-core loop (no TMA / tensor cores). */
+int b2r_debug_scores_simt(b2r_index* h, int q, const float* queries, int normalize, float* out,
+                          void* stream);
+/* Kernel launches issued by this library since load (all streams). */
+int64_t b2r_debug_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2RETR_H_ */

@@ -1,0 +1,553 @@
+// index.cu — opaque index handle + search orchestration behind the C ABI (include/b2retr.h).
+//
+// Mirrors the faiss objects the reference builds in FAISSIndex._create_index
+// (faiss_retrieval.py:44-81) and drives through .train/.add/.search
+// (faiss_retrieval.py:93, :118, :155).
+//
+// Flat search pipeline (all on the caller's stream, no allocation, no host sync):
+//   prep_queries -> [GMAX sample scan -> kth_value => tau]  (large corpus)
+//                   [DUMP scan -> kth_value + compaction]    (small corpus, "dense")
+//                -> FILTER scan (score >= tau -> candidate buffers)
+//                -> select_rescore (sort, provable rescore window, exact fp32, id map)
+#include <math.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "internal.h"
+
+namespace b2r {
+
+static thread_local std::string t_error;
+std::atomic<long long> g_launches{0};
+
+void set_error(const std::string& msg) { t_error = msg; }
+int fail(int code, const std::string& msg) {
+  t_error = msg;
+  return code;
+}
+
+}  // namespace b2r
+
+using namespace b2r;
+
+struct b2r_index {
+  int kind = 0, d = 0, nlist = 0, pq_m = 0, pq_bits = 0, metric = 0, device = 0;
+  int num_sms = 148;
+  int64_t ntotal = 0, capacity = 0;
+  float* x32 = nullptr;          // [capacity, d] fp32 master rows
+  __nv_bfloat16* x16 = nullptr;  // [capacity, d] bf16 scan rows
+  float* maxnorm = nullptr;      // device scalar: max stored row norm
+  int64_t* ids = nullptr;        // optional id map [n_ids]
+  int64_t n_ids = 0;
+  int64_t label_base = 0;
+  CUtensorMap tmX;
+  bool trained = true;
+  // tunables
+  double eps = 0.00390625 * 1.02;  // 2^-8 (two bf16 roundings per product), 2% slack
+  double cand_factor = 4.0;
+  int cand_cap = 4096;
+  int rescore = 1;
+  int force_path = 0;  // 0 auto, 1 dense, 2 filter (tests)
+  int64_t dense_budget = (int64_t)1 << 30;  // bytes of dumped scores per query chunk
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+    if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// ---- search plan: path + workspace layout for one query chunk ----------------
+struct Plan {
+  bool dense = false;
+  int chunk = 0;        // queries per chunk
+  int MQ = 1, QG = 1, splits = 1, qpad = 0;
+  int tiles = 0;        // corpus tiles
+  int cap = 0;
+  int c_target = 0;
+  // sampling pass
+  int s_tiles = 0, s_stride = 1, s_splits = 1, m_rank = 1;
+  int64_t gstride = 0;
+  int64_t dump_ld = 0;
+  // workspace offsets
+  size_t off_q16 = 0, off_q32 = 0, off_qnorm = 0, off_tau = 0, off_count = 0, off_cscore = 0,
+         off_cidx = 0, off_aux = 0, total = 0;
+};
+
+Plan make_plan(const b2r_index* h, int q, int k, bool have_tau) {
+  Plan pl;
+  const int64_t N = h->ntotal;
+  pl.tiles = (int)ceil_div(N > 0 ? N : 1, kTileRows);
+  pl.cap = h->cand_cap;
+  int ct = (int)llround(h->cand_factor * k);
+  if (ct < 64) ct = 64;
+  const int ct_max = (pl.cap * 5) / 8;  // leave head-room for sampling noise
+  if (ct > ct_max) ct = ct_max;
+  if (ct < k) ct = k;
+  pl.c_target = ct;
+  // dense path when the sampled group maxima cannot resolve the threshold rank
+  const bool small = N < (int64_t)256 * ct;
+  pl.dense = !have_tau && (h->force_path == 1 || (h->force_path == 0 && small));
+  if (h->force_path == 2) pl.dense = false;
+  int chunk = q;
+  if (pl.dense) {
+    pl.dump_ld = (int64_t)align_up((size_t)(N > 0 ? N : 1), 4);
+    int64_t qc = h->dense_budget / (pl.dump_ld * 4);
+    if (qc < 1) qc = 1;
+    if (qc >= 256) qc = qc / 256 * 256;
+    if (qc < chunk) chunk = (int)qc;
+  } else {
+    if (chunk > 8192) chunk = 8192;
+  }
+  pl.chunk = chunk;
+  plan_scan(chunk, pl.tiles, h->num_sms, &pl.MQ, &pl.QG, &pl.splits);
+  pl.qpad = pl.QG * pl.MQ * kQBlock;
+  if (!pl.dense && !have_tau) {
+    int64_t st = ceil_div(N, 2 * (int64_t)ct);
+    if (st < 256) st = 256;
+    if (st > pl.tiles) st = pl.tiles;
+    pl.s_stride = (int)(pl.tiles / st);
+    if (pl.s_stride < 1) pl.s_stride = 1;
+    pl.s_tiles = (int)st;
+    pl.gstride = (int64_t)pl.s_tiles * (kTileRows / kGroupCols);
+    const double frac = (double)pl.s_tiles * kTileRows / (double)N;
+    int m = (int)llround(ct * frac);
+    if (m < 1) m = 1;
+    pl.m_rank = m;
+    int mq, qg;
+    plan_scan(chunk, pl.s_tiles, h->num_sms, &mq, &qg, &pl.s_splits);
+  }
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  pl.off_q16 = take((size_t)pl.qpad * h->d * 2);
+  pl.off_q32 = take((size_t)pl.qpad * h->d * 4);
+  pl.off_qnorm = take((size_t)pl.qpad * 4);
+  pl.off_tau = take((size_t)pl.qpad * 4);
+  pl.off_count = take((size_t)pl.qpad * 4);
+  pl.off_cscore = take((size_t)pl.qpad * pl.cap * 4);
+  pl.off_cidx = take((size_t)pl.qpad * pl.cap * 4);
+  size_t aux = 0;
+  if (pl.dense) aux = (size_t)pl.chunk * pl.dump_ld * 4;
+  else if (!have_tau) aux = (size_t)pl.qpad * pl.gstride * 4;
+  pl.off_aux = take(aux);
+  pl.total = off;
+  return pl;
+}
+
+int ensure_capacity(b2r_index* h, int64_t need, cudaStream_t stream) {
+  if (need <= h->capacity) return B2R_OK;
+  int64_t cap = h->capacity > 0 ? h->capacity + h->capacity / 2 : 0;
+  if (cap < need) cap = need;
+  cap = (int64_t)align_up((size_t)cap, 1024);
+  float* n32 = nullptr;
+  __nv_bfloat16* n16 = nullptr;
+  if (cudaMalloc(&n32, (size_t)cap * h->d * 4) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(B2R_ENOMEM, "cudaMalloc of fp32 corpus failed");
+  }
+  if (cudaMalloc(&n16, (size_t)cap * h->d * 2) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(n32);
+    return fail(B2R_ENOMEM, "cudaMalloc of bf16 corpus failed");
+  }
+  if (h->ntotal > 0) {
+    B2R_CUDA(cudaMemcpyAsync(n32, h->x32, (size_t)h->ntotal * h->d * 4, cudaMemcpyDeviceToDevice, stream));
+    B2R_CUDA(cudaMemcpyAsync(n16, h->x16, (size_t)h->ntotal * h->d * 2, cudaMemcpyDeviceToDevice, stream));
+  }
+  B2R_CUDA(cudaStreamSynchronize(stream));
+  cudaFree(h->x32);
+  cudaFree(h->x16);
+  h->x32 = n32;
+  h->x16 = n16;
+  h->capacity = cap;
+  return B2R_OK;
+}
+
+int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries, int normalize, int k,
+                      float* D, int64_t* I, int32_t* status, float* tau_retry, const float* tau_in,
+                      uint8_t* ws, cudaStream_t stream) {
+  const int d = h->d;
+  __nv_bfloat16* q16 = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_q16);
+  float* q32 = reinterpret_cast<float*>(ws + pl.off_q32);
+  float* qnorm = reinterpret_cast<float*>(ws + pl.off_qnorm);
+  float* tau = reinterpret_cast<float*>(ws + pl.off_tau);
+  int* count = reinterpret_cast<int*>(ws + pl.off_count);
+  float* cscore = reinterpret_cast<float*>(ws + pl.off_cscore);
+  uint32_t* cidx = reinterpret_cast<uint32_t*>(ws + pl.off_cidx);
+  float* aux = reinterpret_cast<float*>(ws + pl.off_aux);
+  int rc;
+  // plan for THIS chunk size (the last chunk may be smaller)
+  int MQ, QG, splits;
+  plan_scan(q, pl.tiles, h->num_sms, &MQ, &QG, &splits);
+  const int qpad = QG * MQ * kQBlock;  // <= pl.qpad
+  if ((rc = launch_prep_queries(queries, q, qpad, d, normalize, q32, q16, qnorm, stream))) return rc;
+  CUtensorMap tmQ;
+  if ((rc = make_tmap_bf16_rows(&tmQ, q16, qpad, d))) return rc;
+  if ((rc = launch_fill_f32(tau, qpad, INFINITY, stream))) return rc;
+
+  ScanParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.Q = q;
+  sp.QG = QG;
+  sp.N = h->ntotal;
+  sp.d = d;
+  sp.tile_first = 0;
+  sp.tile_stride = 1;
+  sp.tile_count = pl.tiles;
+  sp.splits = splits;
+  sp.tau = tau;
+  sp.cand_count = count;
+  sp.cand_score = cscore;
+  sp.cand_idx = cidx;
+  sp.cap = pl.cap;
+
+  if (tau_in) {
+    B2R_CUDA(cudaMemcpyAsync(tau, tau_in, (size_t)q * 4, cudaMemcpyDeviceToDevice, stream));
+  } else if (pl.dense) {
+    ScanParams dp = sp;
+    dp.dump = aux;
+    dp.ld = pl.dump_ld;
+    if ((rc = launch_scan(SCAN_DUMP, MQ, tmQ, h->tmX, dp, h->num_sms, stream))) return rc;
+    const int m = (int64_t)pl.c_target < h->ntotal ? pl.c_target : (int)h->ntotal;
+    if ((rc = launch_kth_value(aux, q, h->ntotal, pl.dump_ld, m, tau, count, cscore, cidx, pl.cap, stream)))
+      return rc;
+  } else {
+    ScanParams gp = sp;
+    gp.tile_stride = pl.s_stride;
+    gp.tile_count = pl.s_tiles;
+    int mq, qg;
+    plan_scan(q, pl.s_tiles, h->num_sms, &mq, &qg, &gp.splits);
+    gp.gmax = aux;
+    gp.gstride = (int)pl.gstride;
+    if ((rc = launch_scan(SCAN_GMAX, MQ, tmQ, h->tmX, gp, h->num_sms, stream))) return rc;
+    if ((rc = launch_kth_value(aux, q, pl.gstride, pl.gstride, pl.m_rank, tau, nullptr, nullptr, nullptr, 0, stream)))
+      return rc;
+  }
+  if (tau_in || !pl.dense) {
+    if ((rc = launch_fill_i32(count, qpad, 0, stream))) return rc;
+    if ((rc = launch_scan(SCAN_FILTER, MQ, tmQ, h->tmX, sp, h->num_sms, stream))) return rc;
+  }
+  SelectParams sel;
+  memset(&sel, 0, sizeof(sel));
+  sel.Q = q;
+  sel.k = k;
+  sel.d = d;
+  sel.cap = pl.cap;
+  sel.N = h->ntotal;
+  sel.cand_count = count;
+  sel.cand_score = cscore;
+  sel.cand_idx = cidx;
+  sel.tau = tau;
+  sel.q32 = q32;
+  sel.qnorm = qnorm;
+  sel.x32 = h->x32;
+  sel.maxnorm = h->maxnorm;
+  sel.eps = (float)h->eps;
+  sel.rescore = h->rescore;
+  sel.ids = (h->ids && h->n_ids >= h->ntotal) ? h->ids : nullptr;
+  sel.label_base = h->label_base;
+  sel.D = D;
+  sel.I = I;
+  sel.status = status;
+  sel.tau_retry = tau_retry;
+  return launch_select_rescore(sel, stream);
+}
+
+}  // namespace
+
+// =============================================================== C ABI =====
+extern "C" {
+
+int b2r_version(void) { return B2R_VERSION; }
+const char* b2r_last_error(void) { return t_error.c_str(); }
+int64_t b2r_debug_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int b2r_index_create(b2r_index** out, int kind, int d, int nlist, int pq_m, int pq_bits, int metric,
+                     int device) {
+  if (!out) return fail(B2R_EINVAL, "index_create: out is NULL");
+  *out = nullptr;
+  if (kind != B2R_KIND_FLAT)
+    return fail(B2R_EUNSUPPORTED, "index_create: only B2R_KIND_FLAT is implemented in this build");
+  if (d < 64 || d > 256 || d % 64 != 0)
+    return fail(B2R_EINVAL, "index_create: d must be a multiple of 64 in [64, 256]");
+  if (metric != B2R_METRIC_IP) return fail(B2R_EUNSUPPORTED, "index_create: flat index supports inner product only");
+  int ndev = 0;
+  B2R_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(B2R_EINVAL, "index_create: bad device ordinal");
+  cudaDeviceProp prop;
+  B2R_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(B2R_EUNSUPPORTED, std::string("index_create: device is sm_") + std::to_string(prop.major) +
+                                      std::to_string(prop.minor) + ", this library is sm_100a only");
+  DeviceGuard g(device);
+  b2r_index* h = new b2r_index();
+  h->kind = kind;
+  h->d = d;
+  h->nlist = nlist;
+  h->pq_m = pq_m;
+  h->pq_bits = pq_bits;
+  h->metric = metric;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  if (cudaMalloc(&h->maxnorm, 256) != cudaSuccess) {
+    delete h;
+    return fail(B2R_ENOMEM, "index_create: cudaMalloc failed");
+  }
+  cudaMemset(h->maxnorm, 0, 256);
+  memset(&h->tmX, 0, sizeof(h->tmX));
+  *out = h;
+  return B2R_OK;
+}
+
+int b2r_index_destroy(b2r_index* h) {
+  if (!h) return B2R_OK;
+  DeviceGuard g(h->device);
+  cudaFree(h->x32);
+  cudaFree(h->x16);
+  cudaFree(h->maxnorm);
+  cudaFree(h->ids);
+  delete h;
+  return B2R_OK;
+}
+
+int b2r_index_reset(b2r_index* h) {
+  if (!h) return fail(B2R_EINVAL, "index_reset: NULL handle");
+  DeviceGuard g(h->device);
+  h->ntotal = 0;
+  B2R_CUDA(cudaMemset(h->maxnorm, 0, 256));
+  return B2R_OK;
+}
+
+int64_t b2r_index_ntotal(const b2r_index* h) { return h ? h->ntotal : 0; }
+int b2r_index_is_trained(const b2r_index* h) { return h ? (h->trained ? 1 : 0) : 0; }
+
+int b2r_index_train(b2r_index* h, int64_t n, const float* x, uint64_t seed, void* stream) {
+  (void)n; (void)x; (void)seed; (void)stream;
+  if (!h) return fail(B2R_EINVAL, "index_train: NULL handle");
+  return B2R_OK;  // flat: always trained (faiss IndexFlat::train is a no-op)
+}
+
+int b2r_index_add(b2r_index* h, int64_t n, const float* x, int normalize, void* stream_) {
+  if (!h) return fail(B2R_EINVAL, "index_add: NULL handle");
+  if (n < 0 || (n > 0 && !x)) return fail(B2R_EINVAL, "index_add: bad arguments");
+  if (n == 0) return B2R_OK;
+  if (h->ntotal + n > 0x7FFFFF00ll) return fail(B2R_EUNSUPPORTED, "index_add: more than 2^31 rows per shard");
+  DeviceGuard g(h->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = ensure_capacity(h, h->ntotal + n, stream);
+  if (rc) return rc;
+  rc = launch_ingest(x, n, h->d, normalize, h->x32 + (size_t)h->ntotal * h->d,
+                     h->x16 + (size_t)h->ntotal * h->d, h->maxnorm, stream);
+  if (rc) return rc;
+  h->ntotal += n;
+  return make_tmap_bf16_rows(&h->tmX, h->x16, h->ntotal, h->d);
+}
+
+int b2r_index_set_ids(b2r_index* h, int64_t n, const int64_t* ids, void* stream_) {
+  if (!h) return fail(B2R_EINVAL, "index_set_ids: NULL handle");
+  DeviceGuard g(h->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n <= 0 || !ids) {
+    B2R_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(h->ids);
+    h->ids = nullptr;
+    h->n_ids = 0;
+    return B2R_OK;
+  }
+  B2R_CUDA(cudaStreamSynchronize(stream));
+  cudaFree(h->ids);
+  h->ids = nullptr;
+  h->n_ids = 0;
+  if (cudaMalloc(&h->ids, (size_t)n * 8) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(B2R_ENOMEM, "index_set_ids: cudaMalloc failed");
+  }
+  B2R_CUDA(cudaMemcpyAsync(h->ids, ids, (size_t)n * 8, cudaMemcpyDeviceToDevice, stream));
+  h->n_ids = n;
+  return B2R_OK;
+}
+
+int b2r_index_set_label_base(b2r_index* h, int64_t base) {
+  if (!h) return fail(B2R_EINVAL, "NULL handle");
+  h->label_base = base;
+  return B2R_OK;
+}
+
+int b2r_index_set_param(b2r_index* h, const char* name, double value) {
+  if (!h || !name) return fail(B2R_EINVAL, "index_set_param: NULL argument");
+  const std::string n(name);
+  if (n == "rescore_eps") { if (value < 0) return fail(B2R_EINVAL, "rescore_eps < 0"); h->eps = value; }
+  else if (n == "cand_factor") { if (value < 1) return fail(B2R_EINVAL, "cand_factor < 1"); h->cand_factor = value; }
+  else if (n == "cand_cap") {
+    const int c = (int)value;
+    if (c < 64 || c > 4096 || (c & (c - 1))) return fail(B2R_EINVAL, "cand_cap must be a power of two in [64,4096]");
+    h->cand_cap = c;
+  }
+  else if (n == "rescore") h->rescore = value != 0;
+  else if (n == "force_path") h->force_path = (int)value;
+  else if (n == "dense_budget") h->dense_budget = (int64_t)value;
+  else return fail(B2R_EINVAL, "index_set_param: unknown parameter " + n);
+  return B2R_OK;
+}
+
+double b2r_index_get_param(const b2r_index* h, const char* name) {
+  if (!h || !name) return NAN;
+  const std::string n(name);
+  if (n == "rescore_eps") return h->eps;
+  if (n == "cand_factor") return h->cand_factor;
+  if (n == "cand_cap") return h->cand_cap;
+  if (n == "rescore") return h->rescore;
+  if (n == "force_path") return h->force_path;
+  if (n == "dense_budget") return (double)h->dense_budget;
+  if (n == "num_sms") return h->num_sms;
+  return NAN;
+}
+
+size_t b2r_index_search_workspace(const b2r_index* h, int q, int k, int nprobe) {
+  (void)nprobe;
+  if (!h || q <= 0 || k <= 0) return 0;
+  // sized for either mode (with or without caller thresholds)
+  const Plan a = make_plan(h, q, k, false);
+  const Plan b = make_plan(h, q, k, true);
+  return a.total > b.total ? a.total : b.total;
+}
+
+int b2r_index_search(b2r_index* h, int q, const float* queries, int normalize, int k, int nprobe,
+                     float* D, int64_t* I, int32_t* status, float* tau_retry, const float* tau_in,
+                     void* workspace, size_t ws_bytes, void* stream_) {
+  (void)nprobe;
+  if (!h) return fail(B2R_EINVAL, "index_search: NULL handle");
+  if (q < 0 || k < 1 || (q > 0 && (!queries || !D || !I))) return fail(B2R_EINVAL, "index_search: bad arguments");
+  if (k > 1024) return fail(B2R_EUNSUPPORTED, "index_search: k must be <= 1024");
+  if (q == 0) return B2R_OK;
+  if (!h->trained) return fail(B2R_ESTATE, "index_search: index is not trained");
+  DeviceGuard g(h->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const Plan pl = make_plan(h, q, k, tau_in != nullptr);
+  if (!workspace || ws_bytes < pl.total)
+    return fail(B2R_ENOMEM, "index_search: workspace too small (need " + std::to_string(pl.total) + " bytes)");
+  if (((uintptr_t)workspace & 255) != 0) return fail(B2R_EINVAL, "index_search: workspace must be 256-byte aligned");
+  if (h->ntotal == 0) {
+    // empty index: every slot is empty (faiss returns -1 labels)
+    int rc = launch_fill_f32(D, (int64_t)q * k, -3.4028234663852886e38f, stream);
+    if (rc) return rc;
+    B2R_CUDA(cudaMemsetAsync(I, 0xFF, (size_t)q * k * 8, stream));
+    if (status) B2R_CUDA(cudaMemsetAsync(status, 0, (size_t)q * 4, stream));
+    if (tau_retry) B2R_CUDA(cudaMemsetAsync(tau_retry, 0, (size_t)q * 4, stream));
+    return B2R_OK;
+  }
+  for (int q0 = 0; q0 < q; q0 += pl.chunk) {
+    const int qc = (q - q0) < pl.chunk ? (q - q0) : pl.chunk;
+    int rc = flat_search_chunk(h, pl, qc, queries + (size_t)q0 * h->d, normalize, k, D + (size_t)q0 * k,
+                               I + (size_t)q0 * k, status ? status + q0 : nullptr,
+                               tau_retry ? tau_retry + q0 : nullptr, tau_in ? tau_in + q0 : nullptr,
+                               reinterpret_cast<uint8_t*>(workspace), stream);
+    if (rc) return rc;
+  }
+  return B2R_OK;
+}
+
+int b2r_index_get_vectors(const b2r_index* h, int64_t row0, int64_t n, float* out, void* stream) {
+  if (!h) return fail(B2R_EINVAL, "NULL handle");
+  if (row0 < 0 || n < 0 || row0 + n > h->ntotal) return fail(B2R_EINVAL, "index_get_vectors: range out of bounds");
+  if (n == 0) return B2R_OK;
+  DeviceGuard g(h->device);
+  B2R_CUDA(cudaMemcpyAsync(out, h->x32 + (size_t)row0 * h->d, (size_t)n * h->d * 4, cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return B2R_OK;
+}
+
+int b2r_index_export_centroids(const b2r_index*, float*) { return fail(B2R_EUNSUPPORTED, "no coarse quantiser on this index kind"); }
+int b2r_index_import_centroids(b2r_index*, const float*) { return fail(B2R_EUNSUPPORTED, "no coarse quantiser on this index kind"); }
+int b2r_index_export_codebooks(const b2r_index*, float*) { return fail(B2R_EUNSUPPORTED, "no PQ codebooks on this index kind"); }
+int b2r_index_import_codebooks(b2r_index*, const float*) { return fail(B2R_EUNSUPPORTED, "no PQ codebooks on this index kind"); }
+int b2r_index_list_sizes(const b2r_index*, int64_t*) { return fail(B2R_EUNSUPPORTED, "no inverted lists on this index kind"); }
+
+// ------------------------------------------------------------------ debug ---
+int b2r_debug_scores_tc(b2r_index* h, int q, const float* queries, int normalize, float* out,
+                        void* workspace, size_t ws_bytes, void* stream_) {
+  if (!h || q <= 0 || !queries || !out) return fail(B2R_EINVAL, "debug_scores_tc: bad arguments");
+  if (h->ntotal == 0) return B2R_OK;
+  DeviceGuard g(h->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int MQ, QG, splits;
+  const int tiles = (int)ceil_div(h->ntotal, kTileRows);
+  plan_scan(q, tiles, h->num_sms, &MQ, &QG, &splits);
+  const int qpad = QG * MQ * kQBlock;
+  const size_t need = align_up((size_t)qpad * h->d * 2, 256) + align_up((size_t)qpad * h->d * 4, 256) +
+                      align_up((size_t)qpad * 4, 256);
+  if (!workspace || ws_bytes < need) return fail(B2R_ENOMEM, "debug_scores_tc: workspace too small");
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  __nv_bfloat16* q16 = reinterpret_cast<__nv_bfloat16*>(ws);
+  float* q32 = reinterpret_cast<float*>(ws + align_up((size_t)qpad * h->d * 2, 256));
+  float* qn = reinterpret_cast<float*>(ws + align_up((size_t)qpad * h->d * 2, 256) + align_up((size_t)qpad * h->d * 4, 256));
+  int rc;
+  if ((rc = launch_prep_queries(queries, q, qpad, h->d, normalize, q32, q16, qn, stream))) return rc;
+  CUtensorMap tmQ;
+  if ((rc = make_tmap_bf16_rows(&tmQ, q16, qpad, h->d))) return rc;
+  ScanParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.Q = q;
+  sp.QG = QG;
+  sp.N = h->ntotal;
+  sp.d = h->d;
+  sp.tile_first = 0;
+  sp.tile_stride = 1;
+  sp.tile_count = tiles;
+  sp.splits = splits;
+  sp.dump = out;
+  sp.ld = h->ntotal;
+  return launch_scan(SCAN_DUMP, MQ, tmQ, h->tmX, sp, h->num_sms, stream);
+}
+
+}  // extern "C"
+
+// plain CUDA-core reference of the same bf16 x bf16 -> fp32 contraction (test-only)
+namespace {
+__global__ void scores_simt_kernel(const __nv_bfloat16* __restrict__ x16, int64_t N, int d,
+                                   const float* __restrict__ qin, int Q, int normalize,
+                                   float* __restrict__ out) {
+  const int q = blockIdx.y;
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float qs[1024];
+  __shared__ float s_scale;
+  if (threadIdx.x == 0) {
+    float ss = 0.f;
+    for (int i = 0; i < d; ++i) ss += qin[(size_t)q * d + i] * qin[(size_t)q * d + i];
+    s_scale = (normalize && ss > 0.f) ? 1.0f / sqrtf(ss) : 1.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x)
+    qs[i] = __bfloat162float(__float2bfloat16_rn(qin[(size_t)q * d + i] * s_scale));
+  __syncthreads();
+  if (row >= N) return;
+  float acc = 0.f;
+  for (int i = 0; i < d; ++i) acc = fmaf(qs[i], __bfloat162float(x16[(size_t)row * d + i]), acc);
+  out[(size_t)q * N + row] = acc;
+}
+}  // namespace
+
+extern "C" int b2r_debug_scores_simt(b2r_index* h, int q, const float* queries, int normalize, float* out,
+                                     void* stream_) {
+  if (!h || q <= 0 || !queries || !out) return fail(B2R_EINVAL, "debug_scores_simt: bad arguments");
+  if (h->ntotal == 0) return B2R_OK;
+  DeviceGuard g(h->device);
+  dim3 grid((unsigned)ceil_div(h->ntotal, 256), (unsigned)q);
+  scores_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(h->x16, h->ntotal, h->d, queries, q, normalize, out);
+  B2R_CHECK_LAUNCH("scores_simt_kernel");
+  return B2R_OK;
+}

@@ -1,0 +1,123 @@
+// ingest.cu — row normalisation + fp32/bf16 materialisation for corpus rows and queries.
+//
+// Replaces `embeddings.astype('float32'); faiss.normalize_L2(embeddings)` at
+// faiss_retrieval.py:114-115 (corpus) and :146-147 (queries): per row,
+// if sum(x^2) > 0 then x *= 1/sqrt(sum(x^2)); zero rows stay zero.  The input is never
+// modified (the reference normalises a copy).  HBM-bound elementwise work: one warp per
+// row, 128-bit loads/stores, fp32 master + bf16 scan copy written in the same pass.
+#include "internal.h"
+
+namespace b2r {
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// d % 4 == 0, d <= 1024.  rows_out >= rows_in: rows in [rows_in, rows_out) are zero-filled.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+normalize_rows_kernel(const float* __restrict__ x, int64_t rows_in, int64_t rows_out, int d,
+                      int normalize, float* __restrict__ out32, __nv_bfloat16* __restrict__ out16,
+                      float* __restrict__ norms, float* __restrict__ maxnorm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows_out) return;
+  float4 v[8];
+  const int nvec = d >> 2;  // float4 per row
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane + i * 32;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < nvec && row < rows_in) {
+      v[i] = __ldg(reinterpret_cast<const float4*>(x + row * d) + c);
+      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+  }
+  ss = warp_sum(ss);
+  float scale = 1.f;
+  float stored_norm = sqrtf(ss);
+  if (normalize) {
+    if (ss > 0.f) {
+      scale = 1.0f / sqrtf(ss);
+      stored_norm = 1.0f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      float4 o = make_float4(v[i].x * scale, v[i].y * scale, v[i].z * scale, v[i].w * scale);
+      if (out32) reinterpret_cast<float4*>(out32 + row * d)[c] = o;
+      if (out16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y);
+        __nv_bfloat162 hi = __floats2bfloat162_rn(o.z, o.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(out16 + row * d)[c] = pk;
+      }
+    }
+  }
+  if (lane == 0) {
+    if (norms) norms[row] = (row < rows_in) ? stored_norm : 0.f;
+    if (maxnorm && row < rows_in && stored_norm > 0.f && stored_norm < INFINITY)
+      atomicMax(reinterpret_cast<int*>(maxnorm), __float_as_int(stored_norm));
+  }
+}
+
+__global__ void fill_f32_kernel(float* p, int64_t n, float v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+__global__ void fill_i32_kernel(int* p, int64_t n, int v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+}  // namespace
+
+int launch_ingest(const float* x, int64_t n, int d, int normalize, float* out32,
+                  __nv_bfloat16* out16, float* maxnorm, cudaStream_t stream) {
+  if (n <= 0) return B2R_OK;
+  if (d % 4 != 0 || d > 1024) return fail(B2R_EINVAL, "ingest: d must be a multiple of 4, <= 1024");
+  const int64_t blocks = ceil_div(n, kWarpsPerBlock);
+  normalize_rows_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(
+      x, n, n, d, normalize, out32, out16, nullptr, maxnorm);
+  B2R_CHECK_LAUNCH("normalize_rows_kernel");
+  return B2R_OK;
+}
+
+int launch_prep_queries(const float* x, int q, int qpad, int d, int normalize, float* q32,
+                        __nv_bfloat16* q16, float* qnorm, cudaStream_t stream) {
+  if (qpad <= 0) return B2R_OK;
+  if (d % 4 != 0 || d > 1024) return fail(B2R_EINVAL, "queries: d must be a multiple of 4, <= 1024");
+  const int64_t blocks = ceil_div(qpad, kWarpsPerBlock);
+  normalize_rows_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(
+      x, q, qpad, d, normalize, q32, q16, qnorm, nullptr);
+  B2R_CHECK_LAUNCH("normalize_rows_kernel(queries)");
+  return B2R_OK;
+}
+
+int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t stream) {
+  if (n <= 0) return B2R_OK;
+  const int blocks = (int)(ceil_div(n, 256) < 1184 ? ceil_div(n, 256) : 1184);
+  fill_f32_kernel<<<blocks, 256, 0, stream>>>(p, n, v);
+  B2R_CHECK_LAUNCH("fill_f32_kernel");
+  return B2R_OK;
+}
+int launch_fill_i32(int* p, int64_t n, int v, cudaStream_t stream) {
+  if (n <= 0) return B2R_OK;
+  const int blocks = (int)(ceil_div(n, 256) < 1184 ? ceil_div(n, 256) : 1184);
+  fill_i32_kernel<<<blocks, 256, 0, stream>>>(p, n, v);
+  B2R_CHECK_LAUNCH("fill_i32_kernel");
+  return B2R_OK;
+}
+
+}  // namespace b2r

@@ -1,0 +1,116 @@
+// internal.h — shared declarations between the .cu translation units of libb2retr.so
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/b2retr.h"
+
+namespace b2r {
+
+// ---------------------------------------------------------------- errors ---
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define B2R_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return ::b2r::fail(B2R_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
+  } while (0)
+#define B2R_CHECK_LAUNCH(name)                                                              \
+  do {                                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess)                                                                  \
+      return ::b2r::fail(B2R_ECUDA, std::string("launch ") + name + ": " +                  \
+                                        cudaGetErrorString(_e));                            \
+    ::b2r::count_launch();                                                                  \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------ scan kernel ---
+constexpr int kTileRows = 128;   // corpus rows per UMMA tile (N dimension)
+constexpr int kQBlock = 128;     // queries per UMMA M block (TMEM lanes)
+constexpr int kKChunk = 64;      // bf16 elements per 128-byte swizzle span
+constexpr int kGroupCols = 32;   // GMAX group = one tcgen05.ld chunk of 32 corpus rows
+
+enum ScanMode { SCAN_DUMP = 0, SCAN_GMAX = 1, SCAN_FILTER = 2 };
+
+struct ScanParams {
+  int Q;            // valid queries
+  int QG;           // query groups of 128*MQ rows
+  int64_t N;        // valid corpus rows (rows >= N are zero-filled by TMA and masked)
+  int d;            // embedding dim (multiple of 64, <= 256)
+  int tile_first;   // scanned tile j maps to corpus tile tile_first + j*tile_stride
+  int tile_stride;
+  int tile_count;
+  int splits;       // unit u -> (split = u / QG, qg = u % QG)
+  // FILTER
+  const float* tau;      // [Qpad] candidate threshold (score >= tau passes); +inf for padding
+  int* cand_count;       // [Qpad]
+  float* cand_score;     // [Qpad, cap]
+  uint32_t* cand_idx;    // [Qpad, cap] local row index
+  int cap;
+  // GMAX
+  float* gmax;           // [Qpad, gstride]; entry (q, j*4 + chunk)
+  int gstride;
+  // DUMP
+  float* dump;           // [Q, ld]
+  int64_t ld;
+};
+
+// Builds the 2D bf16 tensor map (rows x d, box 128 rows x 64 cols, 128B swizzle).
+int make_tmap_bf16_rows(CUtensorMap* out, const void* base, int64_t rows, int d);
+int launch_scan(int mode, int MQ, const CUtensorMap& tmQ, const CUtensorMap& tmX,
+                const ScanParams& p, int num_sms, cudaStream_t stream);
+// picks (MQ, splits) for a (Q, tiles) problem
+void plan_scan(int Q, int tile_count, int num_sms, int* MQ, int* QG, int* splits);
+
+// --------------------------------------------------------- ingest / queries ---
+// rows fp32 [n,d] -> (optional L2 normalise) -> fp32 master + bf16 copy; updates *maxnorm
+// (device float, atomic max of the stored rows' L2 norms).
+int launch_ingest(const float* x, int64_t n, int d, int normalize, float* out32,
+                  __nv_bfloat16* out16, float* maxnorm, cudaStream_t stream);
+// queries fp32 [q,d] -> q32 [qpad,d], q16 [qpad,d] (zero padded), qnorm [qpad]
+int launch_prep_queries(const float* x, int q, int qpad, int d, int normalize, float* q32,
+                        __nv_bfloat16* q16, float* qnorm, cudaStream_t stream);
+
+// ------------------------------------------------------------------ select ---
+// per-row m-th largest of vals[r, 0..T) (ld stride) -> tau[r]; if cand_* given, also
+// appends every (val >= tau[r], column) of row r to the candidate buffers (dense path).
+int launch_kth_value(const float* vals, int rows, int64_t T, int64_t ld, int m, float* tau,
+                     int* cand_count, float* cand_score, uint32_t* cand_idx, int cap,
+                     cudaStream_t stream);
+struct SelectParams {
+  int Q, k, d, cap;
+  int64_t N;
+  const int* cand_count;
+  const float* cand_score;
+  const uint32_t* cand_idx;
+  const float* tau;      // [Q] threshold used to build the candidates
+  const float* q32;      // [Qpad, d] prepared fp32 queries
+  const float* qnorm;    // [Qpad]
+  const float* x32;      // [N, d] fp32 master rows
+  const float* maxnorm;  // device scalar
+  float eps;             // relative score error bound
+  int rescore;           // 1: fp32 rescore
+  const int64_t* ids;    // optional id map [N]
+  int64_t label_base;
+  float* D;              // [Q,k]
+  int64_t* I;            // [Q,k]
+  int32_t* status;       // [Q] or null
+  float* tau_retry;      // [Q] or null
+};
+int launch_select_rescore(const SelectParams& p, cudaStream_t stream);
+int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t stream);
+int launch_fill_i32(int* p, int64_t n, int v, cudaStream_t stream);
+
+}  // namespace b2r

@@ -1,0 +1,321 @@
+// select.cu — exact top-k selection around the tensor-core scan.
+//
+// Replaces the heap/reservoir top-k inside faiss `IndexFlatIP::search`
+// (faiss_retrieval.py:155) and the python id remap loop (faiss_retrieval.py:159-160).
+//
+//   kth_value        per-row m-th largest (MSB-first radix select on order-preserving keys)
+//                    -> candidate threshold tau; optionally compacts (val >= tau) into the
+//                    candidate buffers (dense small-corpus path)
+//   select_rescore   per-query: sort candidates by bf16 score, take the provable rescore
+//                    window {s >= s_k - 2E}, exact fp32 re-score from the master rows, final
+//                    sort by (-score, label), id-map gather, write D / I
+//   topk_merge       P sorted per-shard lists -> global top-k (multi-GPU)
+//
+// Integer/compare work; bounded by shared-memory sort latency and the random 1 KB master-row
+// gather, not by tensor throughput.
+#include <float.h>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace b2r {
+namespace {
+
+constexpr int kSelThreads = 512;
+constexpr int kRescoreMax = 2048;  // rescore window slots
+
+__device__ __forceinline__ uint64_t make_key(float score, uint32_t idx) {
+  return ((uint64_t)f2ord(score) << 32) | (uint64_t)(0xFFFFFFFFu - idx);
+}
+__device__ __forceinline__ float key_score(uint64_t k) { return ord2f((uint32_t)(k >> 32)); }
+__device__ __forceinline__ uint32_t key_idx(uint64_t k) { return 0xFFFFFFFFu - (uint32_t)k; }
+
+// in-place bitonic sort, descending, n a power of two, all threads of the block participate
+__device__ void bitonic_desc(uint64_t* s, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t a = s[i], b = s[ixj];
+          const bool up = (i & k) == 0;
+          if (up ? (a < b) : (a > b)) {
+            s[i] = b;
+            s[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// ------------------------------------------------------------- kth_value ---
+__global__ void __launch_bounds__(kSelThreads)
+kth_value_kernel(const float* __restrict__ vals, int64_t T, int64_t ld, int m, float* __restrict__ tau,
+                 int* __restrict__ cand_count, float* __restrict__ cand_score,
+                 uint32_t* __restrict__ cand_idx, int cap) {
+  __shared__ int hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_rem;
+  __shared__ int s_count;
+  const int r = blockIdx.x;
+  const float* row = vals + (size_t)r * ld;
+  float t;
+  if ((int64_t)m >= T) {
+    t = -INFINITY;  // everything qualifies
+  } else {
+    uint32_t prefix = 0, mask = 0;
+    if (threadIdx.x == 0) s_rem = m;
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      for (int64_t i = threadIdx.x; i < T; i += blockDim.x) {
+        const uint32_t key = f2ord(row[i]);
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int rem = s_rem, cum = 0, b = 255;
+        for (; b > 0; --b) {
+          if (cum + hist[b] >= rem) break;
+          cum += hist[b];
+        }
+        s_rem = rem - cum;
+        s_prefix = prefix | ((uint32_t)b << shift);
+      }
+      __syncthreads();
+      prefix = s_prefix;
+      mask |= 255u << shift;
+    }
+    t = ord2f(prefix);
+  }
+  if (threadIdx.x == 0) tau[r] = t;
+  if (cand_count) {
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < T; i += blockDim.x) {
+      const float v = row[i];
+      if (v >= t) {
+        const int slot = atomicAdd(&s_count, 1);
+        if (slot < cap) {
+          cand_score[(size_t)r * cap + slot] = v;
+          cand_idx[(size_t)r * cap + slot] = (uint32_t)i;
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) cand_count[r] = s_count;
+  }
+}
+
+// --------------------------------------------------------- select_rescore ---
+__global__ void __launch_bounds__(kSelThreads)
+select_rescore_kernel(const SelectParams p) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(sm);                       // [cap]
+  uint64_t* rkeys = keys + p.cap;                                          // [kRescoreMax]
+  float* qv = reinterpret_cast<float*>(rkeys + kRescoreMax);               // [d]
+  __shared__ int s_R;
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int c_total = p.cand_count[q];
+  const int c = c_total < p.cap ? c_total : p.cap;
+  const int P = next_pow2(c > 1 ? c : 1);
+  for (int i = tid; i < P; i += blockDim.x) {
+    uint64_t key = 0;  // padding sorts last
+    if (i < c) key = make_key(p.cand_score[(size_t)q * p.cap + i], p.cand_idx[(size_t)q * p.cap + i]);
+    keys[i] = key;
+  }
+  for (int i = tid; i < p.d; i += blockDim.x) qv[i] = p.q32[(size_t)q * p.d + i];
+  if (tid == 0) s_R = 0;
+  __syncthreads();
+  bitonic_desc(keys, P);
+
+  const int kk = (int64_t)p.k < p.N ? p.k : (int)p.N;  // results that exist
+  const float tau_q = p.tau[q];
+  const float E = p.eps * p.qnorm[q] * (*p.maxnorm) * 1.0001f;
+  int status = 0;
+  if (c_total > p.cap) status |= B2R_ST_CAND_OVERFLOW;
+  if (c < kk && tau_q > -INFINITY) status |= B2R_ST_TOO_FEW;
+  const int kth_pos = (c < kk ? c : kk) - 1;
+  const float kth = kth_pos >= 0 ? key_score(keys[kth_pos]) : -INFINITY;
+  const float lim = p.rescore ? kth - 2.0f * E : kth;
+  // rescore window: sorted prefix with score >= lim
+  int local = 0;
+  for (int i = tid; i < c; i += blockDim.x) local += (key_score(keys[i]) >= lim) ? 1 : 0;
+  if (local) atomicAdd(&s_R, local);
+  __syncthreads();
+  int R = s_R;
+  if (R > kRescoreMax) {
+    status |= B2R_ST_RESCORE_OVERFLOW;
+    R = kRescoreMax;
+  }
+  if (p.rescore && c >= kk && kk > 0 && tau_q > lim) status |= B2R_ST_NEED_LOWER_TAU;
+
+  const int R2 = next_pow2(R > 1 ? R : 1);
+  if (p.rescore) {
+    // exact fp32 dot against the master rows: one warp per candidate, 2 candidates in flight
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    for (int i0 = warp * 2; i0 < R; i0 += nwarps * 2) {
+      float acc[2] = {0.f, 0.f};
+      uint32_t idx[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = i0 + u;
+        idx[u] = i < R ? key_idx(keys[i]) : 0u;
+        if (i < R) {
+          const float4* xr = reinterpret_cast<const float4*>(p.x32 + (size_t)idx[u] * p.d);
+          for (int j = lane; j < (p.d >> 2); j += 32) {
+            const float4 xv = __ldg(xr + j);
+            const float4 qq = reinterpret_cast<const float4*>(qv)[j];
+            acc[u] = fmaf(xv.x, qq.x, acc[u]);
+            acc[u] = fmaf(xv.y, qq.y, acc[u]);
+            acc[u] = fmaf(xv.z, qq.z, acc[u]);
+            acc[u] = fmaf(xv.w, qq.w, acc[u]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+        if (lane == 0 && i0 + u < R) rkeys[i0 + u] = make_key(acc[u], idx[u]);
+      }
+    }
+  } else {
+    for (int i = tid; i < R; i += blockDim.x) rkeys[i] = keys[i];
+  }
+  for (int i = R + tid; i < R2; i += blockDim.x) rkeys[i] = 0;
+  __syncthreads();
+  bitonic_desc(rkeys, R2);
+
+  const int avail = R < kk ? R : kk;
+  for (int j = tid; j < p.k; j += blockDim.x) {
+    float dv;
+    int64_t iv;
+    if (j < avail) {
+      const uint64_t key = rkeys[j];
+      const uint32_t idx = key_idx(key);
+      dv = key_score(key);
+      iv = p.ids ? p.ids[idx] : (p.label_base + (int64_t)idx);
+    } else {
+      dv = -FLT_MAX;
+      iv = (p.ids && p.N > 0) ? p.ids[p.N - 1] : -1;  // reference: id_map[-1] wrap-around
+    }
+    p.D[(size_t)q * p.k + j] = dv;
+    p.I[(size_t)q * p.k + j] = iv;
+  }
+  if (tid == 0) {
+    if (p.status) p.status[q] = status;
+    if (p.tau_retry) {
+      float tr = lim;
+      if (status & B2R_ST_TOO_FEW) tr = -INFINITY;
+      else if (status & B2R_ST_CAND_OVERFLOW) tr = fmaxf(lim, tau_q);
+      p.tau_retry[q] = tr;
+    }
+  }
+}
+
+// -------------------------------------------------------------- topk_merge ---
+__global__ void __launch_bounds__(kSelThreads)
+topk_merge_kernel(int P, int k, const float* __restrict__ D_all, const int64_t* __restrict__ I_all,
+                  size_t shard_stride, float* __restrict__ D_out, int64_t* __restrict__ I_out,
+                  int largest) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(sm);
+  const int q = blockIdx.x;
+  const int n = P * k;
+  const int n2 = next_pow2(n > 1 ? n : 1);
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    uint64_t key = 0;
+    if (i < n) {
+      const int s = i / k, j = i % k;
+      const size_t off = (size_t)s * shard_stride + (size_t)q * k + j;
+      if (I_all[off] >= 0) {
+        const float v = D_all[off];
+        key = ((uint64_t)f2ord(largest ? v : -v) << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)i);
+      }
+    }
+    keys[i] = key;
+  }
+  __syncthreads();
+  bitonic_desc(keys, n2);
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const uint64_t key = keys[j];
+    if (key != 0) {
+      const int i = (int)(0xFFFFFFFFu - (uint32_t)key);
+      const size_t off = (size_t)(i / k) * shard_stride + (size_t)q * k + (i % k);
+      D_out[(size_t)q * k + j] = D_all[off];
+      I_out[(size_t)q * k + j] = I_all[off];
+    } else {
+      D_out[(size_t)q * k + j] = largest ? -FLT_MAX : FLT_MAX;
+      I_out[(size_t)q * k + j] = -1;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_kth_value(const float* vals, int rows, int64_t T, int64_t ld, int m, float* tau,
+                     int* cand_count, float* cand_score, uint32_t* cand_idx, int cap,
+                     cudaStream_t stream) {
+  if (rows <= 0) return B2R_OK;
+  if (m < 1) m = 1;
+  kth_value_kernel<<<rows, kSelThreads, 0, stream>>>(vals, T, ld, m, tau, cand_count, cand_score,
+                                                     cand_idx, cap);
+  B2R_CHECK_LAUNCH("kth_value_kernel");
+  return B2R_OK;
+}
+
+int launch_select_rescore(const SelectParams& p, cudaStream_t stream) {
+  if (p.Q <= 0) return B2R_OK;
+  if (p.cap < 1 || (p.cap & (p.cap - 1)) != 0 || p.cap > 4096)
+    return fail(B2R_EINVAL, "select: cap must be a power of two <= 4096");
+  if (p.k > kRescoreMax / 2) return fail(B2R_EUNSUPPORTED, "select: k must be <= 1024");
+  if (p.d % 4 != 0) return fail(B2R_EINVAL, "select: d must be a multiple of 4");
+  const size_t smem = (size_t)p.cap * 8 + (size_t)kRescoreMax * 8 + (size_t)p.d * 4;
+  static bool configured[64] = {};
+  int dev = 0;
+  B2R_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    B2R_CUDA(cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  4096 * 8 + kRescoreMax * 8 + 1024 * 4));
+    configured[dev & 63] = true;
+  }
+  select_rescore_kernel<<<p.Q, kSelThreads, smem, stream>>>(p);
+  B2R_CHECK_LAUNCH("select_rescore_kernel");
+  return B2R_OK;
+}
+
+}  // namespace b2r
+
+extern "C" int b2r_topk_merge(int P, int q, int k, const float* D_all, const int64_t* I_all,
+                              float* D_out, int64_t* I_out, int largest, void* stream) {
+  using namespace b2r;
+  if (P < 1 || q < 0 || k < 1) return fail(B2R_EINVAL, "topk_merge: bad sizes");
+  if ((int64_t)P * k > 8192) return fail(B2R_EUNSUPPORTED, "topk_merge: P*k must be <= 8192");
+  if (q == 0) return B2R_OK;
+  int n2 = 1;
+  while (n2 < P * k) n2 <<= 1;
+  const size_t smem = (size_t)n2 * 8;
+  static bool configured[64] = {};
+  int dev = 0;
+  B2R_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    B2R_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  8192 * 8));
+    configured[dev & 63] = true;
+  }
+  topk_merge_kernel<<<q, kSelThreads, smem, (cudaStream_t)stream>>>(
+      P, k, D_all, I_all, (size_t)q * k, D_out, I_out, largest);
+  B2R_CHECK_LAUNCH("topk_merge_kernel");
+  return B2R_OK;
+}

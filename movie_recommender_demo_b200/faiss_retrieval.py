@@ -1,0 +1,473 @@
+"""Drop-in for the reference `faiss_retrieval` module, backed by libb2retr.so on a B200.
+
+Same public surface as the reference (faiss_retrieval.py:14-369): `FAISSIndex` with
+`train / add / search / batch_search / save / load / get_stats` and the attributes
+`dimension, index_type, nlist, nprobe, use_gpu, index, id_map`; `TwoStageRetriever`.
+`FAISSIndex.index` is a faiss-shaped object (`ntotal`, `is_trained`, `nprobe`, `train`,
+`add`, `search -> (D, I)`), because callers read `faiss_index.index.ntotal`
+(train.py:231, inference.py:156).
+
+What changes underneath: vectors live in HBM (fp32 master + bf16 scan copy), normalisation,
+the score contraction (tcgen05), top-k selection, fp32 re-scoring and the id remap
+(`id_map[idx]`, faiss_retrieval.py:159-160) all run in hand-written sm_100a kernels.
+There is no CPU path: without a CUDA device / the built library every call raises.
+
+Documented deviations from the reference:
+  * `use_gpu` is accepted and ignored - the index is always on the GPU.
+  * 'HNSW' raises NotImplementedError (graph ANN is outside the hot-path scope).
+  * extra keyword-only constructor arguments with reference-preserving defaults:
+    `device`, `pq_m`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import pickle
+import struct
+import time
+import warnings
+from pathlib import Path
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["FAISSIndex", "TwoStageRetriever", "IndexFlatIP", "METRIC_INNER_PRODUCT", "METRIC_L2"]
+
+METRIC_INNER_PRODUCT = _lib.METRIC_IP
+METRIC_L2 = _lib.METRIC_L2
+_RETRY_BITS = _lib.ST_TOO_FEW | _lib.ST_NEED_LOWER_TAU | _lib.ST_CAND_OVERFLOW
+_MAX_RETRIES = 8
+
+
+def _stream_ptr(torch, device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _DeviceIndex:
+    """faiss-shaped handle over a `b2r_index` (one GPU)."""
+
+    kind = _lib.KIND_FLAT
+    metric = METRIC_INNER_PRODUCT
+
+    def __init__(self, d: int, *, nlist: int = 0, pq_m: int = 0, pq_bits: int = 0, device=None):
+        torch = _lib.require_cuda()
+        self._torch = torch
+        self._lib = _lib.load()
+        self.d = int(d)
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        torch.cuda.init()
+        torch.zeros(1, device=self.device)  # make sure the primary context exists
+        h = C.c_void_p()
+        _lib.check(self._lib.b2r_index_create(C.byref(h), self.kind, self.d, int(nlist), int(pq_m),
+                                              int(pq_bits), self.metric, self.device.index))
+        self._h = h
+        self._ws = None
+        self._ids_set = False
+        self.last_status = None  # per-query status bits of the most recent search (numpy)
+        self.last_retries = 0
+
+    # ------------------------------------------------------------ lifetime
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._lib.b2r_index_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ---------------------------------------------------------- properties
+    @property
+    def ntotal(self) -> int:
+        return int(self._lib.b2r_index_ntotal(self._h))
+
+    @property
+    def is_trained(self) -> bool:
+        return bool(self._lib.b2r_index_is_trained(self._h))
+
+    def set_param(self, name: str, value: float) -> None:
+        _lib.check(self._lib.b2r_index_set_param(self._h, name.encode(), float(value)))
+
+    def get_param(self, name: str) -> float:
+        return float(self._lib.b2r_index_get_param(self._h, name.encode()))
+
+    # ------------------------------------------------------------- helpers
+    def _to_device_f32(self, x, what: str):
+        """numpy (any float) or torch tensor -> contiguous fp32 CUDA tensor [n, d] (a copy
+        only when needed; the caller's array is never written)."""
+        torch = self._torch
+        if isinstance(x, torch.Tensor):
+            t = x.detach()
+            if t.dim() != 2 or t.shape[1] != self.d:
+                raise ValueError(f"{what}: expected shape [n, {self.d}], got {tuple(t.shape)}")
+            return t.to(device=self.device, dtype=torch.float32).contiguous()
+        a = np.asarray(x)
+        if a.ndim != 2 or a.shape[1] != self.d:
+            raise ValueError(f"{what}: expected shape [n, {self.d}], got {a.shape}")
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        return torch.from_numpy(a).to(self.device, non_blocking=False)
+
+    def _workspace(self, nbytes: int):
+        torch = self._torch
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ---------------------------------------------------------- faiss API
+    def train(self, x) -> None:
+        xt = self._to_device_f32(x, "train")
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._lib.b2r_index_train(self._h, xt.shape[0], xt.data_ptr(), 1234,
+                                                 _stream_ptr(self._torch, self.device)))
+
+    def add(self, x, normalize: bool = False) -> None:
+        """faiss `index.add(x)`; `normalize=True` fuses faiss.normalize_L2 into the ingest."""
+        xt = self._to_device_f32(x, "add")
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._lib.b2r_index_add(self._h, xt.shape[0], xt.data_ptr(), int(bool(normalize)),
+                                               _stream_ptr(self._torch, self.device)))
+        self._ids_set = False
+
+    def reset(self) -> None:
+        _lib.check(self._lib.b2r_index_reset(self._h))
+        self._ids_set = False
+
+    def set_ids(self, ids) -> None:
+        """Device-side id map: search returns ids[label] (None clears)."""
+        torch = self._torch
+        with torch.cuda.device(self.device):
+            sp = _stream_ptr(torch, self.device)
+            if ids is None:
+                _lib.check(self._lib.b2r_index_set_ids(self._h, 0, None, sp))
+                self._ids_set = False
+                return
+            t = ids if isinstance(ids, torch.Tensor) else torch.as_tensor(np.asarray(ids, dtype=np.int64))
+            t = t.to(device=self.device, dtype=torch.int64).contiguous()
+            _lib.check(self._lib.b2r_index_set_ids(self._h, t.numel(), t.data_ptr(), sp))
+            torch.cuda.current_stream(self.device).synchronize()
+            self._ids_set = True
+
+    def set_label_base(self, base: int) -> None:
+        _lib.check(self._lib.b2r_index_set_label_base(self._h, int(base)))
+
+    def search_device(self, q, k: int, *, normalize: bool = False, nprobe: int = 0, tau=None,
+                      want_status: bool = True):
+        """Asynchronous search on device tensors. Returns (D, I, status, tau_retry) CUDA tensors."""
+        torch = self._torch
+        qt = self._to_device_f32(q, "search")
+        nq = qt.shape[0]
+        k = int(k)
+        with torch.cuda.device(self.device):
+            D = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+            I = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+            status = torch.zeros(nq, dtype=torch.int32, device=self.device) if want_status else None
+            tau_retry = torch.empty(nq, dtype=torch.float32, device=self.device) if want_status else None
+            if nq == 0:
+                return D, I, status, tau_retry
+            need = int(self._lib.b2r_index_search_workspace(self._h, nq, k, int(nprobe)))
+            ws = self._workspace(need)
+            _lib.check(self._lib.b2r_index_search(
+                self._h, nq, qt.data_ptr(), int(bool(normalize)), k, int(nprobe), D.data_ptr(), I.data_ptr(),
+                status.data_ptr() if status is not None else None,
+                tau_retry.data_ptr() if tau_retry is not None else None,
+                tau.data_ptr() if tau is not None else None,
+                ws.data_ptr(), ws.numel(), _stream_ptr(torch, self.device)))
+        return D, I, status, tau_retry
+
+    def search(self, x, k: int, *, normalize: bool = False, nprobe: int = 0, return_device: bool = False):
+        """faiss `index.search(x, k) -> (D, I)`; numpy in, numpy out (CUDA tensors accepted).
+
+        Queries the kernels flag as "not provably exact" (threshold too high / candidate
+        overflow) are re-run with the threshold the device suggests; that needs the status on
+        the host, which rides along with the result copy."""
+        torch = self._torch
+        qt = self._to_device_f32(x, "search")
+        D, I, status, tau_retry = self.search_device(qt, k, normalize=normalize, nprobe=nprobe)
+        st = status.cpu().numpy() if status is not None else np.zeros(qt.shape[0], np.int32)
+        retries = 0
+        prev_tau = None
+        while retries < _MAX_RETRIES:
+            bad = np.nonzero(st & _RETRY_BITS)[0]
+            if bad.size == 0:
+                break
+            bad_t = torch.as_tensor(bad, device=self.device)
+            tau = tau_retry.index_select(0, bad_t).contiguous()
+            tau_host = tau.cpu().numpy()
+            if prev_tau is not None and prev_tau.shape == tau_host.shape and np.array_equal(prev_tau, tau_host):
+                break  # no progress (e.g. a tie group larger than the candidate buffer)
+            prev_tau = tau_host
+            D2, I2, st2, tr2 = self.search_device(qt.index_select(0, bad_t), k, normalize=normalize,
+                                                  nprobe=nprobe, tau=tau)
+            D.index_copy_(0, bad_t, D2)
+            I.index_copy_(0, bad_t, I2)
+            tau_retry.index_copy_(0, bad_t, tr2)
+            st[bad] = st2.cpu().numpy()
+            retries += 1
+        self.last_status = st
+        self.last_retries = retries
+        if (st != 0).any():
+            warnings.warn(f"b200 search: {int((st != 0).sum())} queries not provably exact "
+                          f"(status bits {sorted(set(int(s) for s in st if s))})")
+        if return_device:
+            return D, I
+        return D.cpu().numpy(), I.cpu().numpy()
+
+    def reconstruct_n(self, i0: int, n: int):
+        """fp32 master rows [i0, i0+n) as a CUDA tensor (faiss `reconstruct_n`)."""
+        torch = self._torch
+        out = torch.empty((n, self.d), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.b2r_index_get_vectors(self._h, int(i0), int(n), out.data_ptr(),
+                                                       _stream_ptr(torch, self.device)))
+        return out
+
+    # test-only: the full bf16 score matrix via the tcgen05 dump mode / a CUDA-core loop
+    def debug_scores(self, x, impl: str = "tc", normalize: bool = False):
+        torch = self._torch
+        qt = self._to_device_f32(x, "debug_scores")
+        out = torch.empty((qt.shape[0], self.ntotal), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            sp = _stream_ptr(torch, self.device)
+            if impl == "tc":
+                ws = self._workspace(((qt.shape[0] + 255) // 256 * 256) * self.d * 8 + (1 << 16))
+                _lib.check(self._lib.b2r_debug_scores_tc(self._h, qt.shape[0], qt.data_ptr(), int(normalize),
+                                                         out.data_ptr(), ws.data_ptr(), ws.numel(), sp))
+            else:
+                _lib.check(self._lib.b2r_debug_scores_simt(self._h, qt.shape[0], qt.data_ptr(), int(normalize),
+                                                           out.data_ptr(), sp))
+        return out
+
+
+class IndexFlatIP(_DeviceIndex):
+    """Exact inner-product index (faiss.IndexFlatIP, faiss_retrieval.py:48)."""
+    kind = _lib.KIND_FLAT
+    metric = METRIC_INNER_PRODUCT
+
+
+_NATIVE_MAGIC = b"B2RIDX01"
+
+
+class FAISSIndex:
+    """Reference-compatible wrapper (faiss_retrieval.py:14-256)."""
+
+    verbose = True  # the reference prints progress lines; set False to silence them
+
+    def __init__(self, dimension: int, index_type: str = 'IVF', nlist: int = 100, nprobe: int = 10,
+                 use_gpu: bool = False, *, device=None, pq_m: int = 8):
+        self.dimension = dimension
+        self.index_type = index_type
+        self.nlist = nlist
+        self.nprobe = nprobe
+        self.use_gpu = use_gpu
+        self._device = device
+        self._pq_m = pq_m
+        self.index = None
+        self.id_map: List = []
+        self._ids_all_int = True
+        self._create_index()
+
+    def _say(self, msg: str) -> None:
+        if self.verbose:
+            print(msg)
+
+    def _create_index(self) -> None:
+        kind = self.index_type
+        if kind == 'Flat':
+            self.index = IndexFlatIP(self.dimension, device=self._device)
+        elif kind in ('IVF', 'IVFPQ'):
+            from . import ivf  # noqa: WPS433 (kept separate: optional index families)
+            self.index = ivf.create(self, kind)
+        elif kind == 'HNSW':
+            raise NotImplementedError(
+                "index_type='HNSW' is outside the B200 hot-path scope (graph ANN); use 'Flat', 'IVF' or 'IVFPQ'")
+        else:
+            raise ValueError(f"Unknown index type: {self.index_type}")
+        self._say(f"Created {self.index_type} index with dimension {self.dimension}")
+
+    # ---------------------------------------------------------------- train
+    def train(self, embeddings) -> None:
+        if self.index.is_trained:
+            return
+        self._say(f"Training index on {len(embeddings)} samples...")
+        t0 = time.time()
+        self.index.train(embeddings)
+        self._say(f"Index trained in {time.time() - t0:.2f}s")
+
+    # ------------------------------------------------------------------ add
+    def add(self, embeddings, ad_ids: Optional[List] = None) -> None:
+        # the reference trains on the raw input before normalising it (faiss_retrieval.py:107-115)
+        if not self.index.is_trained:
+            self.train(embeddings)
+        n = len(embeddings)
+        self._say(f"Adding {n} embeddings to index...")
+        t0 = time.time()
+        self.index.add(embeddings, normalize=True)
+        if ad_ids is None:
+            start = len(self.id_map)
+            ad_ids = range(start, start + n)
+        else:
+            ad_ids = list(ad_ids)
+            if self._ids_all_int:
+                self._ids_all_int = all(isinstance(a, (int, np.integer)) for a in ad_ids)
+        self.id_map.extend(ad_ids)
+        self._sync_ids()
+        self._say(f"Added embeddings in {time.time() - t0:.2f}s")
+        self._say(f"Total index size: {self.index.ntotal}")
+
+    def _sync_ids(self) -> None:
+        """Mirror id_map on the device when it is a plain int list of the right length."""
+        if self._ids_all_int and len(self.id_map) == self.index.ntotal and len(self.id_map) > 0:
+            try:
+                arr = np.asarray(self.id_map, dtype=np.int64)
+            except (OverflowError, ValueError, TypeError):
+                self._ids_all_int = False
+                self.index.set_ids(None)
+                return
+            self.index.set_ids(arr)
+        else:
+            self.index.set_ids(None)
+
+    # --------------------------------------------------------------- search
+    def search(self, query_embeddings, k: int = 100, return_distances: bool = True):
+        t0 = time.time()
+        nprobe = self.nprobe if hasattr(self.index, 'nprobe') else 0
+        if nprobe:
+            self.index.nprobe = self.nprobe
+        distances, labels = self.index.search(query_embeddings, k, normalize=True, nprobe=nprobe)
+        if self.index._ids_set:
+            ad_ids = labels  # already id_map[label] (device gather)
+        else:
+            # non-integer ids: host gather with python's negative-index wrap (id_map[-1])
+            table = np.empty(len(self.id_map), dtype=object)
+            table[:] = self.id_map
+            ad_ids = table[labels]
+            try:
+                ad_ids = np.array(ad_ids.tolist())
+            except Exception:
+                pass
+        ms = (time.time() - t0) * 1000
+        self._say(f"Search completed in {ms:.2f}ms for {len(query_embeddings)} queries")
+        if return_distances:
+            return ad_ids, distances
+        return ad_ids
+
+    def batch_search(self, query_embeddings, k: int = 100, batch_size: int = 1000):
+        ids_parts, dist_parts = [], []
+        for lo in range(0, len(query_embeddings), batch_size):
+            ids, dist = self.search(query_embeddings[lo:lo + batch_size], k)
+            ids_parts.append(ids)
+            dist_parts.append(dist)
+        return np.vstack(ids_parts), np.vstack(dist_parts)
+
+    # ------------------------------------------------------------ save/load
+    def save(self, filepath: str) -> None:
+        """Index file (native container) + the reference's pickled `.metadata` side-car
+        (same keys as faiss_retrieval.py:209-219)."""
+        Path(filepath).parent.mkdir(parents=True, exist_ok=True)
+        state = self.index.state_dict() if hasattr(self.index, "state_dict") else {}
+        n = self.index.ntotal
+        vecs = self.index.reconstruct_n(0, n).cpu().numpy() if n else np.zeros((0, self.dimension), np.float32)
+        with open(filepath, "wb") as f:
+            f.write(_NATIVE_MAGIC)
+            blob = pickle.dumps({"index_type": self.index_type, "dimension": self.dimension,
+                                 "ntotal": n, "state": state}, protocol=4)
+            f.write(struct.pack("<Q", len(blob)))
+            f.write(blob)
+            f.write(vecs.astype(np.float32, copy=False).tobytes())
+        with open(filepath + '.metadata', 'wb') as f:
+            pickle.dump({'dimension': self.dimension, 'index_type': self.index_type, 'nlist': self.nlist,
+                         'nprobe': self.nprobe, 'id_map': list(self.id_map)}, f)
+        self._say(f"Index saved to {filepath}")
+
+    def load(self, filepath: str) -> None:
+        with open(filepath + '.metadata', 'rb') as f:
+            meta = pickle.load(f)
+        self.dimension = meta['dimension']
+        self.index_type = meta['index_type']
+        self.nlist = meta['nlist']
+        self.nprobe = meta['nprobe']
+        with open(filepath, "rb") as f:
+            magic = f.read(8)
+            if magic != _NATIVE_MAGIC:
+                raise ValueError(f"{filepath}: not a b200 index file (faiss-format import is not available "
+                                 "in this build)")
+            (blen,) = struct.unpack("<Q", f.read(8))
+            head = pickle.loads(f.read(blen))
+            vecs = np.frombuffer(f.read(), dtype=np.float32).reshape(head["ntotal"], head["dimension"])
+        verbose, self.verbose = self.verbose, False
+        try:
+            self._create_index()
+        finally:
+            self.verbose = verbose
+        if head.get("state") and hasattr(self.index, "load_state_dict"):
+            self.index.load_state_dict(head["state"])
+        if len(vecs):
+            self.index.add(vecs, normalize=False)  # stored rows are already normalised
+        self.id_map = list(meta['id_map'])
+        self._ids_all_int = all(isinstance(a, (int, np.integer)) for a in self.id_map)
+        self._sync_ids()
+        self._say(f"Index loaded from {filepath}")
+        self._say(f"Index size: {self.index.ntotal}")
+
+    def get_stats(self) -> Dict:
+        return {
+            'index_type': self.index_type,
+            'dimension': self.dimension,
+            'num_vectors': self.index.ntotal,
+            'is_trained': self.index.is_trained,
+            'nlist': self.nlist if hasattr(self, 'nlist') else None,
+            'nprobe': self.nprobe if hasattr(self, 'nprobe') else None,
+        }
+
+
+class TwoStageRetriever:
+    """Stage 1 on the B200 kernels, stage 2 = whatever ranker module the caller passes
+    (reference: faiss_retrieval.py:259-369)."""
+
+    def __init__(self, two_tower_model, transformer_ranker, faiss_index: FAISSIndex, device: str = None):
+        import torch
+        if device is None:
+            device = 'cuda' if torch.cuda.is_available() else 'cpu'
+        self.two_tower_model = two_tower_model.to(device).eval()
+        self.transformer_ranker = transformer_ranker.to(device).eval() if transformer_ranker is not None else None
+        self.faiss_index = faiss_index
+        self.device = device
+
+    def retrieve_and_rank(self, user_categorical, user_numerical, stage1_k: int = 500, stage2_k: int = 10,
+                          ad_features_lookup: Dict = None) -> Tuple[List, List]:
+        import torch
+        say = self.faiss_index._say
+        with torch.no_grad():
+            say("\n=== Stage 1: Candidate Generation ===")
+            t0 = time.time()
+            user_emb = self.two_tower_model.get_user_embeddings(user_categorical.to(self.device),
+                                                                user_numerical.to(self.device))
+            # the embedding stays on the device: no .cpu().numpy() round trip (faiss_retrieval.py:316)
+            candidate_ids, distances = self.faiss_index.search(user_emb, k=stage1_k)
+            stage1_ms = (time.time() - t0) * 1000
+            say(f"Stage 1 completed in {stage1_ms:.2f}ms")
+            say(f"Retrieved {stage1_k} candidates")
+
+            say("\n=== Stage 2: Transformer Ranking ===")
+            t1 = time.time()
+            if ad_features_lookup is None or self.transformer_ranker is None:
+                say("Warning: No ad features provided, skipping stage 2")
+                return candidate_ids[0].tolist(), distances[0].tolist()
+            batch_user_cat = user_categorical.repeat(stage1_k, 1).to(self.device)
+            batch_user_num = user_numerical.repeat(stage1_k, 1).to(self.device)
+            # the reference scores an all-zero placeholder here (faiss_retrieval.py:345)
+            batch_ad_cat = torch.zeros(stage1_k, 20, dtype=torch.long, device=self.device)
+            predictions = self.transformer_ranker(batch_user_cat, batch_ad_cat, batch_user_num)
+            ctr = torch.sigmoid(predictions['ctr']).cpu().numpy()
+            order = np.argsort(ctr)[::-1][:stage2_k]
+            final_ids = candidate_ids[0][order].tolist()
+            final_scores = ctr[order].tolist()
+            stage2_ms = (time.time() - t1) * 1000
+            say(f"Stage 2 completed in {stage2_ms:.2f}ms")
+            say(f"Final {stage2_k} ads selected")
+            say(f"\n=== Total Time: {stage1_ms + stage2_ms:.2f}ms ===")
+            return final_ids, final_scores
