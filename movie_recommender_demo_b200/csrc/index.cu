@@ -51,6 +51,10 @@ struct b2r_index {
   int rescore = 1;
   int force_path = 0;  // 0 auto, 1 dense, 2 filter (tests)
   int64_t dense_budget = (int64_t)1 << 30;  // bytes of dumped scores per query chunk
+  // optional CUDA-event timing of the dominant (filter scan) kernel, for bench.py's roofline
+  int profile = 0;
+  std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
+  size_t prof_used = 0;
 };
 
 namespace {
@@ -239,7 +243,13 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
   }
   if (tau_in || !pl.dense) {
     if ((rc = launch_fill_i32(count, qpad, 0, stream))) return rc;
+    const bool prof = h->profile && h->prof_used + 2 <= h->prof_ev.size();
+    if (prof) cudaEventRecord(h->prof_ev[h->prof_used], stream);
     if ((rc = launch_scan(SCAN_FILTER, MQ, tmQ, h->tmX, sp, h->num_sms, stream))) return rc;
+    if (prof) {
+      cudaEventRecord(h->prof_ev[h->prof_used + 1], stream);
+      h->prof_used += 2;
+    }
   }
   SelectParams sel;
   memset(&sel, 0, sizeof(sel));
@@ -320,6 +330,7 @@ int b2r_index_destroy(b2r_index* h) {
   cudaFree(h->x16);
   cudaFree(h->maxnorm);
   cudaFree(h->ids);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   delete h;
   return B2R_OK;
 }
@@ -400,6 +411,18 @@ int b2r_index_set_param(b2r_index* h, const char* name, double value) {
   else if (n == "rescore") h->rescore = value != 0;
   else if (n == "force_path") h->force_path = (int)value;
   else if (n == "dense_budget") h->dense_budget = (int64_t)value;
+  else if (n == "profile") {
+    // value > 0: (re)start timing of up to `value` filter-scan launches; 0: stop
+    DeviceGuard g(h->device);
+    h->profile = value > 0;
+    h->prof_used = 0;
+    const size_t want = value > 0 ? (size_t)value * 2 : 0;
+    while (h->prof_ev.size() < want) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return fail(B2R_ECUDA, "cudaEventCreate failed");
+      h->prof_ev.push_back(e);
+    }
+  }
   else return fail(B2R_EINVAL, "index_set_param: unknown parameter " + n);
   return B2R_OK;
 }
@@ -414,6 +437,20 @@ double b2r_index_get_param(const b2r_index* h, const char* name) {
   if (n == "force_path") return h->force_path;
   if (n == "dense_budget") return (double)h->dense_budget;
   if (n == "num_sms") return h->num_sms;
+  if (n == "scan_ms_avg" || n == "scan_launches") {
+    // mean device time of the timed filter-scan launches (synchronises on their events)
+    double total = 0;
+    size_t cnt = 0;
+    for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+      float ms = 0;
+      if (cudaEventSynchronize(h->prof_ev[i + 1]) != cudaSuccess) break;
+      if (cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]) != cudaSuccess) break;
+      total += ms;
+      ++cnt;
+    }
+    if (n == "scan_launches") return (double)cnt;
+    return cnt ? total / cnt : NAN;
+  }
   return NAN;
 }
 

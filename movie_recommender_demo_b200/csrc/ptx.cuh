@@ -45,15 +45,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug traps (kernel aborts with an error) instead of
 // hanging the GPU.  ~2^31 cycles ≈ 1 s at 2 GHz; legitimate waits are << 1 ms.
+// The report path is out of line so that each inlined wait stays a few instructions
+// (instruction-cache footprint matters for the warp-specialised kernels).
+static __device__ __noinline__ void mbar_timeout(int tag, uint32_t parity) {
+  printf("b2r: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x,
+         (int)threadIdx.x, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > (1ll << 31)) {
-      printf("b2r: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x,
-             (int)threadIdx.x, parity);
-      __trap();
-    }
+    if (clock64() - t0 > (1ll << 31)) mbar_timeout(tag, parity);
   }
 }
 
@@ -173,6 +176,11 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// same for IEEE fp16 operands (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16_f32(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // ----------------------------------------------------------- misc utilities

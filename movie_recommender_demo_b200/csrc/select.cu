@@ -117,27 +117,31 @@ kth_value_kernel(const float* __restrict__ vals, int64_t T, int64_t ld, int m, f
 }
 
 // --------------------------------------------------------- select_rescore ---
-__global__ void __launch_bounds__(kSelThreads)
+// One CTA (1024 threads) per query:
+//   1. candidates -> smem keys (ord(score) << 32 | ~row)
+//   2. k-th largest bf16 score by MSB-first radix select over the smem keys (no full sort)
+//   3. rescore window = {score >= kth - 2E}, compacted (order irrelevant)
+//   4. exact fp32 dot per window entry: one warp per row, 4 rows in flight per warp
+//   5. bitonic sort of the window by (-score, row), gather ids, write top-k
+constexpr int kSel2Threads = 1024;
+
+__global__ void __launch_bounds__(kSel2Threads)
 select_rescore_kernel(const SelectParams p) {
   extern __shared__ __align__(16) uint8_t sm[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(sm);                       // [cap]
   uint64_t* rkeys = keys + p.cap;                                          // [kRescoreMax]
   float* qv = reinterpret_cast<float*>(rkeys + kRescoreMax);               // [d]
+  __shared__ int hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_rem;
   __shared__ int s_R;
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
   const int c_total = p.cand_count[q];
   const int c = c_total < p.cap ? c_total : p.cap;
-  const int P = next_pow2(c > 1 ? c : 1);
-  for (int i = tid; i < P; i += blockDim.x) {
-    uint64_t key = 0;  // padding sorts last
-    if (i < c) key = make_key(p.cand_score[(size_t)q * p.cap + i], p.cand_idx[(size_t)q * p.cap + i]);
-    keys[i] = key;
-  }
+  for (int i = tid; i < c; i += blockDim.x)
+    keys[i] = make_key(p.cand_score[(size_t)q * p.cap + i], p.cand_idx[(size_t)q * p.cap + i]);
   for (int i = tid; i < p.d; i += blockDim.x) qv[i] = p.q32[(size_t)q * p.d + i];
-  if (tid == 0) s_R = 0;
-  __syncthreads();
-  bitonic_desc(keys, P);
 
   const int kk = (int64_t)p.k < p.N ? p.k : (int)p.N;  // results that exist
   const float tau_q = p.tau[q];
@@ -145,54 +149,103 @@ select_rescore_kernel(const SelectParams p) {
   int status = 0;
   if (c_total > p.cap) status |= B2R_ST_CAND_OVERFLOW;
   if (c < kk && tau_q > -INFINITY) status |= B2R_ST_TOO_FEW;
-  const int kth_pos = (c < kk ? c : kk) - 1;
-  const float kth = kth_pos >= 0 ? key_score(keys[kth_pos]) : -INFINITY;
+
+  // ---- k-th largest candidate score (rank m = min(kk, c)), radix select on the high word
+  const int m = c < kk ? c : kk;
+  float kth = -INFINITY;
+  if (m >= 1) {
+    uint32_t prefix = 0, mask = 0;
+    if (tid == 0) s_rem = m;
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      if (tid < 256) hist[tid] = 0;
+      __syncthreads();
+      for (int i = tid; i < c; i += blockDim.x) {
+        const uint32_t key = (uint32_t)(keys[i] >> 32);
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int rem = s_rem, cum = 0, b = 255;
+        for (; b > 0; --b) {
+          if (cum + hist[b] >= rem) break;
+          cum += hist[b];
+        }
+        s_rem = rem - cum;
+        s_prefix = prefix | ((uint32_t)b << shift);
+      }
+      __syncthreads();
+      prefix = s_prefix;
+      mask |= 255u << shift;
+    }
+    kth = ord2f(prefix);
+  }
   const float lim = p.rescore ? kth - 2.0f * E : kth;
-  // rescore window: sorted prefix with score >= lim
-  int local = 0;
-  for (int i = tid; i < c; i += blockDim.x) local += (key_score(keys[i]) >= lim) ? 1 : 0;
-  if (local) atomicAdd(&s_R, local);
+  if (p.rescore && c >= kk && kk > 0 && tau_q > lim) status |= B2R_ST_NEED_LOWER_TAU;
+
+  // ---- compact the rescore window into rkeys (unordered)
+  if (tid == 0) s_R = 0;
+  __syncthreads();
+  for (int i = tid; i < c; i += blockDim.x) {
+    const uint64_t key = keys[i];
+    if (key_score(key) >= lim) {
+      const int pos = atomicAdd(&s_R, 1);
+      if (pos < kRescoreMax) rkeys[pos] = key;
+    }
+  }
   __syncthreads();
   int R = s_R;
   if (R > kRescoreMax) {
+    // window larger than the buffer: keep the best kRescoreMax by bf16 score (not provably exact)
     status |= B2R_ST_RESCORE_OVERFLOW;
+    __syncthreads();
+    const int P = next_pow2(c > 1 ? c : 1);
+    for (int i = c + tid; i < P; i += blockDim.x) keys[i] = 0;
+    __syncthreads();
+    bitonic_desc(keys, P);
+    for (int i = tid; i < kRescoreMax; i += blockDim.x) rkeys[i] = keys[i];
     R = kRescoreMax;
+    __syncthreads();
   }
-  if (p.rescore && c >= kk && kk > 0 && tau_q > lim) status |= B2R_ST_NEED_LOWER_TAU;
 
-  const int R2 = next_pow2(R > 1 ? R : 1);
   if (p.rescore) {
-    // exact fp32 dot against the master rows: one warp per candidate, 2 candidates in flight
+    // exact fp32 dot against the master rows: one warp per row, 4 rows in flight per warp
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    for (int i0 = warp * 2; i0 < R; i0 += nwarps * 2) {
-      float acc[2] = {0.f, 0.f};
-      uint32_t idx[2];
+    const int nv = p.d >> 2;
+    for (int i0 = warp * 4; i0 < R; i0 += nwarps * 4) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t idx[4];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int i = i0 + u;
-        idx[u] = i < R ? key_idx(keys[i]) : 0u;
-        if (i < R) {
-          const float4* xr = reinterpret_cast<const float4*>(p.x32 + (size_t)idx[u] * p.d);
-          for (int j = lane; j < (p.d >> 2); j += 32) {
-            const float4 xv = __ldg(xr + j);
-            const float4 qq = reinterpret_cast<const float4*>(qv)[j];
-            acc[u] = fmaf(xv.x, qq.x, acc[u]);
-            acc[u] = fmaf(xv.y, qq.y, acc[u]);
-            acc[u] = fmaf(xv.z, qq.z, acc[u]);
-            acc[u] = fmaf(xv.w, qq.w, acc[u]);
-          }
+      for (int u = 0; u < 4; ++u) idx[u] = (i0 + u < R) ? key_idx(rkeys[i0 + u]) : 0u;
+      for (int j = lane; j < nv; j += 32) {
+        const float4 qq = reinterpret_cast<const float4*>(qv)[j];
+        float4 xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          xv[u] = (i0 + u < R) ? __ldg(reinterpret_cast<const float4*>(p.x32 + (size_t)idx[u] * p.d) + j)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          acc[u] = fmaf(xv[u].x, qq.x, acc[u]);
+          acc[u] = fmaf(xv[u].y, qq.y, acc[u]);
+          acc[u] = fmaf(xv[u].z, qq.z, acc[u]);
+          acc[u] = fmaf(xv[u].w, qq.w, acc[u]);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < 4; ++u) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
-        if (lane == 0 && i0 + u < R) rkeys[i0 + u] = make_key(acc[u], idx[u]);
+      }
+      __syncwarp();
+      if (lane < 4 && i0 + lane < R) {
+        const float a = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+        const uint32_t ix = lane == 0 ? idx[0] : lane == 1 ? idx[1] : lane == 2 ? idx[2] : idx[3];
+        rkeys[i0 + lane] = make_key(a, ix);
       }
     }
-  } else {
-    for (int i = tid; i < R; i += blockDim.x) rkeys[i] = keys[i];
   }
+  const int R2 = next_pow2(R > 1 ? R : 1);
   for (int i = R + tid; i < R2; i += blockDim.x) rkeys[i] = 0;
   __syncthreads();
   bitonic_desc(rkeys, R2);
@@ -290,7 +343,7 @@ int launch_select_rescore(const SelectParams& p, cudaStream_t stream) {
                                   4096 * 8 + kRescoreMax * 8 + 1024 * 4));
     configured[dev & 63] = true;
   }
-  select_rescore_kernel<<<p.Q, kSelThreads, smem, stream>>>(p);
+  select_rescore_kernel<<<p.Q, kSel2Threads, smem, stream>>>(p);
   B2R_CHECK_LAUNCH("select_rescore_kernel");
   return B2R_OK;
 }

@@ -1,0 +1,243 @@
+"""GPU parity tests of the Flat path: every call goes FAISSIndex -> ctypes -> libb2retr.so
+(C ABI) -> sm_100a kernels, and is compared with the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GAP_TOL = 1e-6      # adjacent-score gap below which order may differ from the oracle (fp32 accumulation order)
+SCORE_RTOL = 1e-3   # north_star tolerance; after the fp32 rescore the observed error is ~1e-7
+
+
+@pytest.fixture(scope="module")
+def fr(built_lib):
+    import torch
+    assert torch.cuda.is_available()
+    from movie_recommender_demo_b200 import faiss_retrieval
+    faiss_retrieval.FAISSIndex.verbose = False
+    return faiss_retrieval
+
+
+def _bf16(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def _parity(fr, N, Q, k, d=256, seed=0, force_path=0, unit=False):
+    from oracle.compare import compare_topk
+    from oracle.flat import OracleFAISSIndex
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((N, d)).astype(np.float32)
+    q = rng.standard_normal((Q, d)).astype(np.float32)
+    g = fr.FAISSIndex(d, 'Flat')
+    if force_path:
+        g.index.set_param("force_path", force_path)
+    g.add(x)
+    o = OracleFAISSIndex(d, 'Flat')
+    o.add(x)
+    ids, dist = g.search(q, k=k)
+    rid, rd = o.search(q, k=k, extra=32)
+    res = compare_topk(ids, dist, rid, rd, k, gap_tol=GAP_TOL, score_rtol=SCORE_RTOL)
+    assert (g.index.last_status == 0).all()
+    assert dist.dtype == np.float32 and ids.dtype == np.int64
+    return res
+
+
+@pytest.mark.parametrize("N,Q,d", [(256, 16, 256), (1000, 1, 256), (5000, 130, 256), (70001, 300, 128),
+                                   (33, 5, 192), (100000, 64, 64)])
+def test_tcgen05_score_tile_matches_bf16_reference(fr, N, Q, d):
+    """Dump mode of the scan kernel == bf16-operand / fp32-accumulate contraction."""
+    rng = np.random.default_rng(N + Q)
+    x = rng.standard_normal((N, d)).astype(np.float32)
+    q = rng.standard_normal((Q, d)).astype(np.float32)
+    idx = fr.IndexFlatIP(d)
+    idx.add(x)
+    tc = idx.debug_scores(q, "tc").cpu().numpy()
+    simt = idx.debug_scores(q, "simt").cpu().numpy()
+    ref = _bf16(q).astype(np.float64) @ _bf16(x).astype(np.float64).T
+    scale = np.abs(ref).max()
+    assert np.abs(tc - ref).max() <= 2e-6 * scale * np.sqrt(d)
+    assert np.abs(simt - ref).max() <= 2e-6 * scale * np.sqrt(d)
+
+
+@pytest.mark.parametrize("N,Q,k", [(20000, 37, 50), (3000, 5, 500), (100, 3, 500), (1, 2, 10), (4096, 8, 100)])
+def test_dense_path_matches_oracle(fr, N, Q, k):
+    _parity(fr, N, Q, k, seed=N)
+
+
+def test_config1_shape_100k_ads_512_queries_top500(fr):
+    """BASELINE config 1 shape: IndexFlatIP top-500 over 100k embeddings, 512 queries."""
+    res = _parity(fr, 100000, 512, 500, seed=11)
+    assert res["exact_positions"] > 0.95 * 512 * 500
+
+
+@pytest.mark.parametrize("N,Q,k,force", [(300000, 8, 100, 2), (1000000, 64, 500, 0), (1000000, 1, 500, 0),
+                                          (600000, 300, 500, 0), (150000, 3, 10, 2)])
+def test_filter_path_matches_oracle(fr, N, Q, k, force):
+    _parity(fr, N, Q, k, seed=N + Q, force_path=force)
+
+
+def test_ingest_normalises_like_faiss_and_never_mutates_input(fr):
+    from oracle.flat import normalize_L2
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((1000, 256)) * 3).astype(np.float64)
+    x[5] = 0
+    x0 = x.copy()
+    g = fr.FAISSIndex(256, 'Flat')
+    g.add(x)
+    assert (x == x0).all()
+    got = g.index.reconstruct_n(0, 1000).cpu().numpy()
+    ref = normalize_L2(x.astype(np.float32))
+    assert np.abs(got - ref).max() < 2e-7
+    assert (got[5] == 0).all()                      # zero-norm rows stay zero
+    raw = fr.IndexFlatIP(256)
+    raw.add(x.astype(np.float32))                   # faiss-level add: no normalisation, bit-exact copy
+    assert np.array_equal(raw.reconstruct_n(0, 1000).cpu().numpy(), x.astype(np.float32))
+
+
+def test_wrapper_semantics(fr):
+    """ids first, default ids continue, k > ntotal pads with id_map[-1] / -FLT_MAX, object ids."""
+    from oracle.flat import NEG_FLT_MAX, OracleFAISSIndex
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((300, 64)).astype(np.float32)
+    q = rng.standard_normal((4, 64)).astype(np.float32)
+    g = fr.FAISSIndex(64, 'Flat')
+    o = OracleFAISSIndex(64, 'Flat')
+    for t in (g, o):
+        t.add(x[:100])
+        t.add(x[100:], ad_ids=list(range(1000, 1200)))
+    assert g.id_map == o.id_map and g.index.ntotal == 300 and g.index.is_trained
+    ids, d = g.search(q, k=320)
+    oid, od = o.search(q, k=320)
+    assert np.array_equal(ids[:, :300], oid[:, :300])
+    assert (ids[:, 300:] == 1199).all() and (d[:, 300:] == NEG_FLT_MAX).all()
+    np.testing.assert_allclose(d[:, :300], od[:, :300], atol=3e-7)
+    assert g.search(q, k=5, return_distances=False).shape == (4, 5)
+    bi, bd = g.batch_search(q, k=7, batch_size=3)
+    assert np.array_equal(bi, oid[:, :7])
+    assert g.get_stats() == {'index_type': 'Flat', 'dimension': 64, 'num_vectors': 300, 'is_trained': True,
+                             'nlist': 100, 'nprobe': 10}
+    # arbitrary python ids -> host mapping, still id_map[idx]
+    s = fr.FAISSIndex(64, 'Flat')
+    s.add(x[:50], ad_ids=[f"ad{i}" for i in range(50)])
+    sid, _ = s.search(q, k=3)
+    so = OracleFAISSIndex(64, 'Flat')
+    so.add(x[:50], ad_ids=[f"ad{i}" for i in range(50)])
+    assert np.array_equal(sid, so.search(q, k=3)[0])
+    # faiss-level object: (D, I) order; labels when no id map is attached
+    raw = fr.IndexFlatIP(64)
+    raw.add(x, normalize=True)
+    D, I = raw.search(q, 5, normalize=True)
+    assert D.shape == (4, 5) and I.dtype == np.int64 and I.max() < 300
+    assert np.array_equal(np.asarray(g.id_map)[I], ids[:, :5])
+
+
+def test_accepts_cuda_tensors_and_empty_inputs(fr):
+    import torch
+    g = fr.FAISSIndex(128, 'Flat')
+    D, I = g.index.search(np.zeros((2, 128), np.float32), 4)
+    assert (I == -1).all()                          # empty index
+    x = torch.randn(5000, 128, device="cuda")
+    g.add(x)
+    q = torch.randn(3, 128, device="cuda")
+    ids, d = g.search(q, k=10)
+    ids2, d2 = g.search(q.cpu().numpy(), k=10)
+    assert np.array_equal(ids, ids2) and np.array_equal(d, d2)
+    ids0, d0 = g.index.search(np.zeros((0, 128), np.float32), 4)
+    assert ids0.shape == (0, 4)
+
+
+def test_duplicates_and_zero_queries(fr):
+    """Exact duplicate rows tie -> canonical order by label; an all-zero query scores 0 everywhere."""
+    from oracle.compare import compare_topk
+    from oracle.flat import OracleFAISSIndex
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((2000, 64)).astype(np.float32)
+    x[500:520] = x[7]
+    q = rng.standard_normal((3, 64)).astype(np.float32)
+    q[1] = x[7]
+    g = fr.FAISSIndex(64, 'Flat')
+    o = OracleFAISSIndex(64, 'Flat')
+    g.add(x), o.add(x)
+    ids, d = g.search(q, k=30)
+    rid, rd = o.search(q, k=30, extra=32)
+    compare_topk(ids, d, rid, rd, 30, gap_tol=GAP_TOL)
+    assert set(ids[1, :21].tolist()) == {7, *range(500, 520)}
+
+
+def test_full_size_round_trip_properties(fr):
+    """BASELINE config 2 size (1M x 256, top-500): size-independent properties — every query that
+    IS a corpus row retrieves itself first with score 1, scores are sorted, ids unique, and a
+    second search returns bit-identical results."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(1)
+    N, d = 1_000_000, 256
+    x = torch.randn((N, d), generator=g, device="cuda")
+    idx = fr.FAISSIndex(d, 'Flat')
+    idx.add(x)
+    rows = torch.tensor([0, 17, 123456, 999999], device="cuda")
+    ids, dist = idx.search(x[rows], k=500)
+    assert ids[:, 0].tolist() == rows.tolist()
+    np.testing.assert_allclose(dist[:, 0], 1.0, atol=2e-6)
+    assert (np.diff(dist, axis=1) <= 0).all()
+    assert all(len(set(r.tolist())) == 500 for r in ids)
+    ids2, dist2 = idx.search(x[rows], k=500)
+    assert np.array_equal(ids, ids2) and np.array_equal(dist, dist2)
+    # rescored scores equal an fp32 torch dot of the normalised rows
+    xn = torch.nn.functional.normalize(x[rows], dim=1)
+    ref = (xn[:, None, :] * torch.nn.functional.normalize(x[torch.from_numpy(ids).cuda()], dim=2)).sum(-1)
+    np.testing.assert_allclose(dist, ref.cpu().numpy(), atol=3e-6)
+    assert (idx.index.last_status == 0).all()
+
+
+def test_threshold_retry_path_recovers(fr):
+    """Force a far-too-high candidate threshold: the status bits must flag it and the host retry
+    loop must still return the oracle's answer."""
+    import torch
+    from oracle.compare import compare_topk
+    from oracle.flat import OracleFAISSIndex
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((200000, 64)).astype(np.float32)
+    q = rng.standard_normal((4, 64)).astype(np.float32)
+    g = fr.FAISSIndex(64, 'Flat')
+    g.add(x)
+    tau = torch.full((4,), 0.9, device="cuda")
+    D, I, st, tr = g.index.search_device(q, 50, normalize=True, tau=tau)
+    assert (st.cpu().numpy() & 1).all()             # B2R_ST_TOO_FEW
+    g.index.set_param("cand_factor", 1.0)           # tight threshold -> NEED_LOWER_TAU retries likely
+    g.index.set_param("force_path", 2)
+    ids, d = g.search(q, k=50)
+    o = OracleFAISSIndex(64, 'Flat')
+    o.add(x)
+    rid, rd = o.search(q, k=50, extra=32)
+    compare_topk(ids, d, rid, rd, 50, gap_tol=GAP_TOL)
+    assert (g.index.last_status == 0).all()
+
+
+def test_topk_merge_matches_unsharded(fr, built_lib):
+    """P logical shards on one device + b2r_topk_merge == unsharded search."""
+    import torch
+    from movie_recommender_demo_b200 import _lib
+    rng = np.random.default_rng(10)
+    N, d, Q, k, P = 40000, 64, 9, 100, 4
+    x = rng.standard_normal((N, d)).astype(np.float32)
+    q = rng.standard_normal((Q, d)).astype(np.float32)
+    full = fr.IndexFlatIP(d)
+    full.add(x, normalize=True)
+    Dref, Iref = full.search(q, k, normalize=True)
+    Ds, Is = [], []
+    for s in range(P):
+        lo, hi = s * N // P, (s + 1) * N // P
+        sh = fr.IndexFlatIP(d)
+        sh.add(x[lo:hi], normalize=True)
+        sh.set_label_base(lo)
+        D, I = sh.search(q, k, normalize=True, return_device=True)
+        Ds.append(D), Is.append(I)
+    D_all = torch.stack(Ds).contiguous()
+    I_all = torch.stack(Is).contiguous()
+    D_out = torch.empty((Q, k), dtype=torch.float32, device="cuda")
+    I_out = torch.empty((Q, k), dtype=torch.int64, device="cuda")
+    _lib.check(built_lib.b2r_topk_merge(P, Q, k, D_all.data_ptr(), I_all.data_ptr(), D_out.data_ptr(),
+                                        I_out.data_ptr(), 1, int(torch.cuda.current_stream().cuda_stream)))
+    assert np.array_equal(I_out.cpu().numpy(), Iref)
+    assert np.array_equal(D_out.cpu().numpy(), Dref)

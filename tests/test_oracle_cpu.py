@@ -1,0 +1,108 @@
+"""CPU tests: the oracle against the golden fixtures / brute force, and the comparator."""
+import numpy as np
+import pytest
+
+from oracle import towers as otowers
+from oracle.compare import compare_topk, recall_at_k
+from oracle.flat import NEG_FLT_MAX, OracleFAISSIndex, OracleIndexFlatIP, normalize_L2, topk_desc
+from weights import CONFIGS, make_inputs, make_state
+
+GOLDEN = __import__("pathlib").Path(__file__).parent / "golden"
+
+
+@pytest.mark.parametrize("cfg_name", ["cfg1", "small"])
+def test_oracle_towers_match_reference_golden(cfg_name):
+    """oracle/towers.py vs outputs of the reference's own two_tower_model.py."""
+    fx = np.load(GOLDEN / f"towers_{cfg_name}.npz")
+    cfg = CONFIGS[cfg_name]
+    state = make_state(cfg, int(fx["seed"]))
+    assert sorted(state.keys()) == sorted(fx["keys"].tolist())
+    ucat, unum, acat = make_inputs(cfg, int(fx["seed"]), fx["ucat"].shape[0])
+    assert (ucat == fx["ucat"]).all() and (acat == fx["acat"]).all() and (unum == fx["unum"]).all()
+    # embedding gather + concat: bit exact
+    assert np.array_equal(otowers.embedding_concat(state, "user_tower", ucat), fx["user_embedding_layer"])
+    assert np.array_equal(otowers.embedding_concat(state, "ad_tower", acat), fx["ad_embedding_layer"])
+    u = otowers.tower_forward(state, "user_tower", ucat, unum)
+    a = otowers.tower_forward(state, "ad_tower", acat)
+    np.testing.assert_allclose(u, fx["user_out"], rtol=0, atol=5e-6)
+    np.testing.assert_allclose(a, fx["ad_out"], rtol=0, atol=5e-6)
+
+
+def test_embedding_out_of_range_raises():
+    cfg = CONFIGS["small"]
+    state = make_state(cfg, 1)
+    ucat, _, _ = make_inputs(cfg, 1, 4)
+    ucat[2, 1] = cfg["user_cards"][1]
+    with pytest.raises(IndexError):
+        otowers.embedding_concat(state, "user_tower", ucat)
+
+
+def test_normalize_l2_semantics():
+    x = np.array([[3, 4], [0, 0], [1e-30, 0]], dtype=np.float32)
+    y = normalize_L2(x.copy())
+    np.testing.assert_allclose(y[0], [0.6, 0.8], rtol=1e-6)
+    assert (y[1] == 0).all()          # zero rows stay zero (faiss fvec_renorm_L2)
+
+
+def test_flat_topk_matches_bruteforce_and_canonical_ties():
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((5000, 32)).astype(np.float32)
+    X[100] = X[7]                       # exact duplicate -> tie broken by label
+    Q = rng.standard_normal((9, 32)).astype(np.float32)
+    o = OracleFAISSIndex(32, 'Flat')
+    o.add(X)
+    ids, d = o.search(Q, k=40)
+    Xn = normalize_L2(X.copy())
+    Qn = normalize_L2(Q.copy())
+    S = Qn @ Xn.T
+    ref = np.argsort(-S, axis=1, kind="stable")[:, :40]
+    assert np.array_equal(ids, ref)
+    assert np.array_equal(d, np.take_along_axis(S, ref, axis=1))
+    assert (np.diff(d, axis=1) <= 0).all()
+
+
+def test_wrapper_semantics_ids_and_empty_slots():
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((30, 8)).astype(np.float64)   # fp64 accepted, never mutated
+    X0 = X.copy()
+    o = OracleFAISSIndex(8, 'Flat')
+    o.add(X[:10])
+    o.add(X[10:], ad_ids=[f"ad{i}" for i in range(20)])   # arbitrary python ids
+    assert (X == X0).all()
+    assert o.id_map[:10] == list(range(10)) and o.id_map[10] == "ad0"   # default ids continue from len(id_map)
+    ids, d = o.search(rng.standard_normal((2, 8)), k=40)
+    assert ids.shape == (2, 40)
+    assert (ids[:, 30:] == "ad19").all()                  # label -1 -> id_map[-1] (faiss_retrieval.py:159-160)
+    assert (d[:, 30:] == NEG_FLT_MAX).all()
+    only_ids = o.search(rng.standard_normal((2, 8)), k=5, return_distances=False)
+    assert only_ids.shape == (2, 5)
+    ids_b, d_b = o.batch_search(rng.standard_normal((7, 8)), k=3, batch_size=2)
+    assert ids_b.shape == (7, 3)
+    with pytest.raises(ValueError, match="Unknown index type: Bogus"):
+        OracleFAISSIndex(8, 'Bogus')
+    assert o.get_stats()["num_vectors"] == 30
+
+
+def test_comparator_accepts_near_tie_permutations_only():
+    ref_d = np.array([[0.9, 0.5, 0.5 - 5e-7, 0.3, 0.2, 0.2 - 1e-7]], dtype=np.float32)
+    ref_i = np.array([[4, 8, 2, 7, 1, 9]])
+    k = 5
+    ok_i = np.array([[4, 2, 8, 7, 9]])       # swap inside the tie run; boundary run may pick 9 instead of 1
+    ok_d = ref_d[:, :k]
+    r = compare_topk(ok_i, ok_d, ref_i, ref_d, k)
+    assert r["tie_positions"] == 3 and r["exact_positions"] == 2
+    with pytest.raises(AssertionError):
+        compare_topk(np.array([[8, 4, 2, 7, 1]]), ok_d, ref_i, ref_d, k)     # real order violation
+    with pytest.raises(AssertionError):
+        compare_topk(np.array([[4, 8, 2, 7, 3]]), ok_d, ref_i, ref_d, k)     # foreign id
+    bad_d = ok_d.copy()
+    bad_d[0, 0] = 0.95
+    with pytest.raises(AssertionError):
+        compare_topk(ok_i, bad_d, ref_i, ref_d, k)
+
+
+def test_topk_desc_k_larger_than_n():
+    S = np.array([[0.1, 0.9, 0.5]], dtype=np.float32)
+    D, I = topk_desc(S, 5)
+    assert I.tolist() == [[1, 2, 0, -1, -1]] and (D[0, 3:] == NEG_FLT_MAX).all()
+    assert recall_at_k(I, I) == 1.0
