@@ -187,7 +187,13 @@ class _DeviceIndex:
         torch = self._torch
         qt = self._to_device_f32(x, "search")
         D, I, status, tau_retry = self.search_device(qt, k, normalize=normalize, nprobe=nprobe)
-        st = status.cpu().numpy() if status is not None else np.zeros(qt.shape[0], np.int32)
+        # results + status ride to pinned host buffers in one batch of async copies, one sync
+        st_h = self._to_pinned(status)
+        D_h = I_h = None
+        if not return_device:
+            D_h, I_h = self._to_pinned(D), self._to_pinned(I)
+        torch.cuda.current_stream(self.device).synchronize()
+        st = st_h.numpy()
         retries = 0
         prev_tau = None
         while retries < _MAX_RETRIES:
@@ -205,8 +211,10 @@ class _DeviceIndex:
             D.index_copy_(0, bad_t, D2)
             I.index_copy_(0, bad_t, I2)
             tau_retry.index_copy_(0, bad_t, tr2)
+            st = st.copy()
             st[bad] = st2.cpu().numpy()
             retries += 1
+            D_h = None  # stale
         self.last_status = st
         self.last_retries = retries
         if (st != 0).any():
@@ -214,7 +222,17 @@ class _DeviceIndex:
                           f"(status bits {sorted(set(int(s) for s in st if s))})")
         if return_device:
             return D, I
-        return D.cpu().numpy(), I.cpu().numpy()
+        if D_h is None:
+            D_h, I_h = self._to_pinned(D), self._to_pinned(I)
+            torch.cuda.current_stream(self.device).synchronize()
+        return D_h.numpy(), I_h.numpy()
+
+    def _to_pinned(self, t):
+        """async device->pinned-host copy (torch's caching host allocator recycles the blocks;
+        the returned numpy view keeps its block alive)."""
+        h = self._torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        return h
 
     def reconstruct_n(self, i0: int, n: int):
         """fp32 master rows [i0, i0+n) as a CUDA tensor (faiss `reconstruct_n`)."""

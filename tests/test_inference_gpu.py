@@ -1,0 +1,144 @@
+"""GPU tests of the callers on either side of the hot path: TwoStageRetriever.retrieve_and_rank
+(faiss_retrieval.py:283-331), AdRecommenderInference.recommend_ads / batch_recommend
+(inference.py:199-331), build-from-tower + FAISSIndex.save/load (training_pipeline.py:488-546)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+class _Enc:
+    def __init__(self, classes):
+        self.classes_ = np.array(classes, dtype=object)
+
+
+class _Scaler:
+    def __init__(self, n):
+        rng = np.random.default_rng(0)
+        self.mean_, self.scale_ = rng.normal(1.0, 0.2, n), rng.uniform(0.5, 1.5, n)
+
+    def transform(self, x):
+        return ((np.asarray(x, dtype=np.float64) - self.mean_) / self.scale_).astype(np.float32)
+
+
+class _Preprocessor:
+    """Duck-typed stand-in for the reference's CriteoDataPreprocessor (CPU ETL, out of scope)."""
+
+    def __init__(self, cfg):
+        self.feature_dims = {}
+        self.label_encoders = {}
+        for i, c in enumerate(cfg["user_cards"] + cfg["ad_cards"]):
+            col = f"C{i + 1}"
+            self.feature_dims[col] = c
+            self.label_encoders[col] = _Enc([f"v{j}" for j in range(c - 1)] + ["missing"])
+        self.numerical_cols = [f"I{i + 1}" for i in range(cfg["numerical_dim"])]
+        self.scaler = _Scaler(cfg["numerical_dim"])
+
+
+@pytest.fixture(scope="module")
+def system(built_lib, tmp_path_factory):
+    import torch
+    from movie_recommender_demo_b200.faiss_retrieval import FAISSIndex
+    from movie_recommender_demo_b200.two_tower_model import TwoTowerModel
+    from weights import CONFIGS, feature_dims, make_inputs, make_state
+    FAISSIndex.verbose = False
+    cfg = CONFIGS["cfg1"]
+    user, ad = feature_dims(cfg)
+    state = make_state(cfg, 31)
+    model = TwoTowerModel(user, ad, cfg["numerical_dim"], cfg["embedding_dim"], cfg["hidden_dims"], cfg["output_dim"])
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in state.items()})
+    model = model.to("cuda").eval()
+    _, _, acat = make_inputs(cfg, 32, 30000)
+    # corpus build (training_pipeline.build_faiss_index shape): AdTower over all rows -> index.add(emb, row ids)
+    embs = []
+    with torch.no_grad():
+        for lo in range(0, len(acat), 4096):
+            embs.append(model.get_ad_embeddings(torch.from_numpy(acat[lo:lo + 4096]).cuda()))
+    ad_emb = torch.cat(embs)
+    index = FAISSIndex(256, 'Flat')
+    index.add(ad_emb, list(range(len(acat))))
+    return dict(cfg=cfg, state=state, model=model, index=index, ad_emb=ad_emb, tmp=tmp_path_factory.mktemp("idx"))
+
+
+def _oracle_stage1(system, ucat, unum, k):
+    from oracle import towers as otowers
+    from oracle.flat import OracleFAISSIndex
+    u = otowers.tower_forward(system["state"], "user_tower", ucat, unum)
+    o = OracleFAISSIndex(256, 'Flat')
+    o.add(system["ad_emb"].cpu().numpy())
+    return u, o
+
+
+def test_two_stage_retriever_stage1_matches_oracle(system):
+    import torch
+    from movie_recommender_demo_b200.faiss_retrieval import TwoStageRetriever
+    from oracle.compare import compare_topk
+    from weights import make_inputs
+    ucat, unum, _ = make_inputs(system["cfg"], 33, 1)
+    r = TwoStageRetriever(system["model"], None, system["index"], device="cuda")
+    ids, scores = r.retrieve_and_rank(torch.from_numpy(ucat), torch.from_numpy(unum), stage1_k=500)
+    assert isinstance(ids, list) and len(ids) == 500 and len(scores) == 500
+    # the oracle searches with the GPU tower's embedding (tower parity is tested separately)
+    with torch.no_grad():
+        u_gpu = system["model"].get_user_embeddings(torch.from_numpy(ucat).cuda(), torch.from_numpy(unum).cuda())
+    _, o = _oracle_stage1(system, ucat, unum, 500)
+    rid, rd = o.search(u_gpu.cpu().numpy(), k=500, extra=32)
+    compare_topk(np.array([ids]), np.array([scores], dtype=np.float32), rid, rd, 500, gap_tol=1e-6)
+
+
+def test_recommend_ads_and_batch_recommend(system):
+    import torch
+    from movie_recommender_demo_b200.inference import AdRecommenderInference
+
+    class _Ranker(torch.nn.Module):        # stock-PyTorch stand-in for the out-of-scope Stage-2 ranker
+        def forward(self, user_cat, ad_cat, user_num):
+            s = ad_cat.float().sum(dim=1)
+            return {'ctr': s, 'engagement': -s, 'revenue': s * 0.5}
+
+    pre = _Preprocessor(system["cfg"])
+    inf = AdRecommenderInference(model_dir="/nonexistent", device="cuda", preprocessor=pre,
+                                 two_tower_model=system["model"], transformer_ranker=_Ranker(),
+                                 faiss_index=system["index"], verbose=False)
+    users = [{'categorical': {f"C{i + 1}": f"v{(3 * u + i) % 5}" for i in range(6)},
+              'numerical': {f"I{i + 1}": float(u + i) for i in range(13)}} for u in range(5)]
+    users[2]['categorical']['C3'] = 'never-seen'            # falls back to 'missing' (inference.py:178-180)
+    rec = inf.recommend_ads(users[0], top_k=10, stage1_k=500)
+    assert set(rec) >= {'ad_ids', 'timing', 'scores'} and len(rec['ad_ids']) == 10
+    assert set(rec['timing']) == {'stage1_ms', 'stage2_ms', 'total_ms'}
+    assert set(rec['scores']) == {'ctr', 'engagement', 'revenue'}
+    assert set(rec['ad_ids']) <= set(rec['candidate_ids'].tolist())
+    batch = inf.batch_recommend(users, top_k=10, stage1_k=500)
+    assert len(batch) == 5
+    # batched stage 1 == one-at-a-time stage 1 (ids and scores)
+    for u, b in zip(users, batch):
+        single = inf.recommend_ads(u, top_k=10, stage1_k=500)
+        assert np.array_equal(single['candidate_ids'], b['candidate_ids'])
+        np.testing.assert_allclose(single['stage1_scores'], b['stage1_scores'], atol=2e-6)
+    # stage-1 parity against the oracle chain (preprocess -> tower -> flat search)
+    from oracle.compare import compare_topk
+    cat, num = inf.preprocess_user_batch(users)
+    with torch.no_grad():
+        u_gpu = system["model"].get_user_embeddings(cat.cuda(), num.cuda()).cpu().numpy()
+    u_ref, o = _oracle_stage1(system, cat.numpy(), num.numpy(), 500)
+    assert np.abs(u_gpu - u_ref).max() < 1e-3
+    rid, rd = o.search(u_gpu, k=500, extra=32)
+    compare_topk(np.stack([b['candidate_ids'] for b in batch]), np.stack([b['stage1_scores'] for b in batch]),
+                 rid, rd, 500, gap_tol=1e-6)
+
+
+def test_save_load_round_trip(system):
+    from movie_recommender_demo_b200.faiss_retrieval import FAISSIndex
+    path = str(system["tmp"] / "faiss_index.bin")
+    system["index"].save(path)
+    import pickle
+    meta = pickle.load(open(path + ".metadata", "rb"))
+    assert set(meta) == {'dimension', 'index_type', 'nlist', 'nprobe', 'id_map'}   # reference keys (:209-219)
+    loaded = FAISSIndex(256, 'Flat', nlist=7, nprobe=3)   # ctor args are overwritten by load, like the reference
+    loaded.load(path)
+    assert loaded.index_type == 'Flat' and loaded.nlist == 100 and loaded.nprobe == 10
+    assert loaded.index.ntotal == system["index"].index.ntotal
+    q = system["ad_emb"][:7]
+    a, da = system["index"].search(q, k=50)
+    b, db = loaded.search(q, k=50)
+    assert np.array_equal(a, b) and np.array_equal(da, db)
+    assert a[:, 0].tolist() == list(range(7))
