@@ -77,7 +77,8 @@ struct Plan {
   int chunk = 0;        // queries per chunk
   int MQ = 1, QG = 1, splits = 1, qpad = 0;
   int tiles = 0;        // corpus tiles
-  int cap = 0;
+  int nseg = 1;         // candidate segments per query
+  int cap_seg = 0;      // slots per segment
   int c_target = 0;
   // sampling pass
   int s_tiles = 0, s_stride = 1, s_splits = 1, m_rank = 1;
@@ -92,10 +93,10 @@ Plan make_plan(const b2r_index* h, int q, int k, bool have_tau) {
   Plan pl;
   const int64_t N = h->ntotal;
   pl.tiles = (int)ceil_div(N > 0 ? N : 1, kTileRows);
-  pl.cap = h->cand_cap;
+  const int cap = h->cand_cap;  // candidates per query the select kernel holds (4096)
   int ct = (int)llround(h->cand_factor * k);
   if (ct < 64) ct = 64;
-  const int ct_max = (pl.cap * 5) / 8;  // leave head-room for sampling noise
+  const int ct_max = (cap * 5) / 8;  // leave head-room for sampling noise
   if (ct > ct_max) ct = ct_max;
   if (ct < k) ct = k;
   pl.c_target = ct;
@@ -116,6 +117,19 @@ Plan make_plan(const b2r_index* h, int q, int k, bool have_tau) {
   pl.chunk = chunk;
   plan_scan(chunk, pl.tiles, h->num_sms, &pl.MQ, &pl.QG, &pl.splits);
   pl.qpad = pl.QG * pl.MQ * kQBlock;
+  if (pl.dense) {
+    pl.nseg = 1;
+    pl.cap_seg = cap;
+  } else {
+    // filter path: one private segment per (query, corpus split[, column half]); sized for the
+    // worst chunk geometry (a smaller last chunk may pick MQ = 1 -> two segments per split)
+    pl.nseg = pl.splits * 2;
+    int per = (int)ceil_div(4 * (int64_t)ct, pl.splits);  // 4x the mean entries per segment
+    int cs = 32;
+    while (cs < per) cs <<= 1;
+    if (cs > cap) cs = cap;
+    pl.cap_seg = cs;
+  }
   if (!pl.dense && !have_tau) {
     int64_t st = ceil_div(N, 2 * (int64_t)ct);
     if (st < 256) st = 256;
@@ -141,9 +155,9 @@ Plan make_plan(const b2r_index* h, int q, int k, bool have_tau) {
   pl.off_q32 = take((size_t)pl.qpad * h->d * 4);
   pl.off_qnorm = take((size_t)pl.qpad * 4);
   pl.off_tau = take((size_t)pl.qpad * 4);
-  pl.off_count = take((size_t)pl.qpad * 4);
-  pl.off_cscore = take((size_t)pl.qpad * pl.cap * 4);
-  pl.off_cidx = take((size_t)pl.qpad * pl.cap * 4);
+  pl.off_count = take((size_t)pl.qpad * pl.nseg * 4);
+  pl.off_cscore = take((size_t)pl.qpad * pl.nseg * pl.cap_seg * 8);
+  pl.off_cidx = pl.off_cscore;
   size_t aux = 0;
   if (pl.dense) aux = (size_t)pl.chunk * pl.dump_ld * 4;
   else if (!have_tau) aux = (size_t)pl.qpad * pl.gstride * 4;
@@ -190,8 +204,7 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
   float* qnorm = reinterpret_cast<float*>(ws + pl.off_qnorm);
   float* tau = reinterpret_cast<float*>(ws + pl.off_tau);
   int* count = reinterpret_cast<int*>(ws + pl.off_count);
-  float* cscore = reinterpret_cast<float*>(ws + pl.off_cscore);
-  uint32_t* cidx = reinterpret_cast<uint32_t*>(ws + pl.off_cidx);
+  uint2* cand = reinterpret_cast<uint2*>(ws + pl.off_cscore);
   float* aux = reinterpret_cast<float*>(ws + pl.off_aux);
   int rc;
   // plan for THIS chunk size (the last chunk may be smaller)
@@ -214,10 +227,14 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
   sp.tile_count = pl.tiles;
   sp.splits = splits;
   sp.tau = tau;
+  // the planned split count fixes the segment geometry; this chunk may use fewer splits
+  if (splits > pl.splits) splits = pl.splits;
+  sp.splits = splits;
   sp.cand_count = count;
-  sp.cand_score = cscore;
-  sp.cand_idx = cidx;
-  sp.cap = pl.cap;
+  sp.cand = cand;
+  sp.nseg = splits * (MQ == 1 ? 2 : 1);
+  sp.cap_seg = pl.cap_seg;
+  int sel_nseg = sp.nseg, sel_cap_seg = pl.cap_seg;
 
   if (tau_in) {
     B2R_CUDA(cudaMemcpyAsync(tau, tau_in, (size_t)q * 4, cudaMemcpyDeviceToDevice, stream));
@@ -227,8 +244,10 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
     dp.ld = pl.dump_ld;
     if ((rc = launch_scan(SCAN_DUMP, MQ, tmQ, h->tmX, dp, h->num_sms, stream))) return rc;
     const int m = (int64_t)pl.c_target < h->ntotal ? pl.c_target : (int)h->ntotal;
-    if ((rc = launch_kth_value(aux, q, h->ntotal, pl.dump_ld, m, tau, count, cscore, cidx, pl.cap, stream)))
+    if ((rc = launch_kth_value(aux, q, h->ntotal, pl.dump_ld, m, tau, count, cand, pl.cap_seg, stream)))
       return rc;
+    sel_nseg = 1;
+    sel_cap_seg = pl.cap_seg;
   } else {
     ScanParams gp = sp;
     gp.tile_stride = pl.s_stride;
@@ -238,11 +257,10 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
     gp.gmax = aux;
     gp.gstride = (int)pl.gstride;
     if ((rc = launch_scan(SCAN_GMAX, MQ, tmQ, h->tmX, gp, h->num_sms, stream))) return rc;
-    if ((rc = launch_kth_value(aux, q, pl.gstride, pl.gstride, pl.m_rank, tau, nullptr, nullptr, nullptr, 0, stream)))
+    if ((rc = launch_kth_value(aux, q, pl.gstride, pl.gstride, pl.m_rank, tau, nullptr, nullptr, 0, stream)))
       return rc;
   }
   if (tau_in || !pl.dense) {
-    if ((rc = launch_fill_i32(count, qpad, 0, stream))) return rc;
     const bool prof = h->profile && h->prof_used + 2 <= h->prof_ev.size();
     if (prof) cudaEventRecord(h->prof_ev[h->prof_used], stream);
     if ((rc = launch_scan(SCAN_FILTER, MQ, tmQ, h->tmX, sp, h->num_sms, stream))) return rc;
@@ -256,11 +274,11 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
   sel.Q = q;
   sel.k = k;
   sel.d = d;
-  sel.cap = pl.cap;
+  sel.nseg = sel_nseg;
+  sel.cap_seg = sel_cap_seg;
   sel.N = h->ntotal;
   sel.cand_count = count;
-  sel.cand_score = cscore;
-  sel.cand_idx = cidx;
+  sel.cand = cand;
   sel.tau = tau;
   sel.q32 = q32;
   sel.qnorm = qnorm;

@@ -53,12 +53,13 @@ struct ScanParams {
   int tile_stride;
   int tile_count;
   int splits;       // unit u -> (split = u / QG, qg = u % QG)
-  // FILTER
+  // FILTER: candidates go to private segments, one per (query, corpus split[, column half]):
+  // exactly one warp ever writes a segment, so an append is a plain store + register counter.
   const float* tau;      // [Qpad] candidate threshold (score >= tau passes); +inf for padding
-  int* cand_count;       // [Qpad]
-  float* cand_score;     // [Qpad, cap]
-  uint32_t* cand_idx;    // [Qpad, cap] local row index
-  int cap;
+  int* cand_count;       // [Qpad, nseg] entries produced per segment (may exceed cap_seg)
+  uint2* cand;           // [Qpad, nseg, cap_seg] (score bits, local row index)
+  int nseg;              // splits * (MQ == 1 ? 2 : 1)
+  int cap_seg;
   // GMAX
   float* gmax;           // [Qpad, gstride]; entry (q, j*4 + chunk)
   int gstride;
@@ -87,14 +88,13 @@ int launch_prep_queries(const float* x, int q, int qpad, int d, int normalize, f
 // per-row m-th largest of vals[r, 0..T) (ld stride) -> tau[r]; if cand_* given, also
 // appends every (val >= tau[r], column) of row r to the candidate buffers (dense path).
 int launch_kth_value(const float* vals, int rows, int64_t T, int64_t ld, int m, float* tau,
-                     int* cand_count, float* cand_score, uint32_t* cand_idx, int cap,
-                     cudaStream_t stream);
+                     int* cand_count, uint2* cand, int cap, cudaStream_t stream);
 struct SelectParams {
-  int Q, k, d, cap;
+  int Q, k, d;
+  int nseg, cap_seg;     // candidate segments per query / slots per segment
   int64_t N;
-  const int* cand_count;
-  const float* cand_score;
-  const uint32_t* cand_idx;
+  const int* cand_count; // [Q, nseg]
+  const uint2* cand;     // [Q, nseg, cap_seg]
   const float* tau;      // [Q] threshold used to build the candidates
   const float* q32;      // [Qpad, d] prepared fp32 queries
   const float* qnorm;    // [Qpad]

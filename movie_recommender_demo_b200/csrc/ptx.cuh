@@ -54,9 +54,14 @@ static __device__ __noinline__ void mbar_timeout(int tag, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > (1ll << 31)) mbar_timeout(tag, parity);
+  long long t0 = 0;
+  for (uint32_t it = 1;; ++it) {
+    if (mbar_try_wait(bar, parity)) return;  // try_wait suspends in hardware for a bounded time
+    if ((it & 255u) == 0) {                  // look at the clock only now and then
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > (1ll << 31)) mbar_timeout(tag, parity);
+    }
   }
 }
 

@@ -28,104 +28,23 @@ namespace b2r {
 
 namespace {
 
-// Per-epilogue-warp staging buffer for FILTER hits (scores, rows, producer lane): hits are
-// compacted with ballots (no atomics in the scan loop) and flushed to the global candidate
-// lists 32 at a time, so the global-atomic round trip is paid once per batch, not per hit.
-constexpr int kStageCap = 128;
-constexpr int kStageBytes = kStageCap * 9;  // float + uint32 + uint8 per entry
-
 template <int MQ>
 struct ScanCfg {
-  static constexpr int NS = (MQ == 1) ? 9 : 5;   // B ring slots (16 KB each)
+  static constexpr int NS = (MQ == 1) ? 9 : 6;   // B ring slots (16 KB each)
   static constexpr int NB = 4 / MQ;              // TMEM accumulator buffers
   static constexpr int A_BYTES = MQ * 4 * 16384;
   static constexpr int B_BYTES = NS * 16384;
   static constexpr int NBARS = 2 * NS + 2 * NB + 2;
-  static constexpr int STAGE_OFF = A_BYTES + B_BYTES + NBARS * 8 + 64;
-  static constexpr int SMEM = 1024 + STAGE_OFF + 8 * kStageBytes + 8 * 8;
+  static constexpr int SMEM = 1024 + A_BYTES + B_BYTES + NBARS * 8 + 64;
 };
 
 constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;
 
-// Per-warp staging area layout in shared memory:
-//   float score[kStageCap] | uint32 row[kStageCap] | uint8 lane[kStageCap]
-// plus a small per-warp header {cnt, qbase} kept in a separate int2 array (warp-uniform values).
-struct StagePtr {
-  uint8_t* base;   // staging arrays of this warp
-  int* hdr;        // hdr[0] = cnt, hdr[1] = qbase (query index of lane 0 for the current unit)
-};
-
-__device__ __noinline__ void stage_flush(const ScanParams* pp, uint8_t* base, int* hdr) {
-  const ScanParams& p = *pp;
-  const int lane = threadIdx.x & 31;
-  const float* sc = reinterpret_cast<const float*>(base);
-  const uint32_t* rw = reinterpret_cast<const uint32_t*>(base + kStageCap * 4);
-  const uint8_t* ln = base + kStageCap * 8;
-  __syncwarp();
-  const int cnt = hdr[0], qbase = hdr[1];
-  for (int i0 = 0; i0 < cnt; i0 += 64) {
-    // two entries per lane in flight: both atomics are issued before either store
-    const int ia = i0 + lane, ib = i0 + 32 + lane;
-    int qa = 0, qb = 0, sa = 0, sb = 0;
-    if (ia < cnt) { qa = qbase + ln[ia]; sa = atomicAdd(p.cand_count + qa, 1); }
-    if (ib < cnt) { qb = qbase + ln[ib]; sb = atomicAdd(p.cand_count + qb, 1); }
-    if (ia < cnt && sa < p.cap) {
-      p.cand_score[(size_t)qa * p.cap + sa] = sc[ia];
-      p.cand_idx[(size_t)qa * p.cap + sa] = rw[ia];
-    }
-    if (ib < cnt && sb < p.cap) {
-      p.cand_score[(size_t)qb * p.cap + sb] = sc[ib];
-      p.cand_idx[(size_t)qb * p.cap + sb] = rw[ib];
-    }
-  }
-  __syncwarp();
-  if (lane == 0) hdr[0] = 0;
-  __syncwarp();
-}
-
-// Slow path of the FILTER epilogue: at least one lane of the warp has a score >= tau among
-// these 8 columns.  Whole warp executes it; hits are compacted with ballots into the warp's
-// staging buffer (no atomics).  Out of line on purpose: one copy in the instruction cache.
-__device__ __noinline__ void filter_slow8(const ScanParams* pp, uint8_t* base, int* hdr, float tau,
-                                          uint32_t row0, int nvalid, float v0, float v1, float v2,
-                                          float v3, float v4, float v5, float v6, float v7) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  float* sc = reinterpret_cast<float*>(base);
-  uint32_t* rw = reinterpret_cast<uint32_t*>(base + kStageCap * 4);
-  uint8_t* ln = base + kStageCap * 8;
-  const float v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
-  int cnt = hdr[0];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool hit = (v[i] >= tau) && (i < nvalid);
-    const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-    if (bal) {
-      if (hit) {
-        const int pos = cnt + __popc(bal & lt_mask);
-        sc[pos] = v[i];
-        rw[pos] = row0 + i;
-        ln[pos] = (uint8_t)lane;
-      }
-      cnt += __popc(bal);
-      if (cnt > kStageCap - 32) {
-        __syncwarp();
-        if (lane == 0) hdr[0] = cnt;
-        stage_flush(pp, base, hdr);
-        cnt = 0;
-      }
-    }
-  }
-  __syncwarp();
-  if (lane == 0) hdr[0] = cnt;
-  __syncwarp();
-}
-
 template <int MODE>
 __device__ __forceinline__ void epi_chunk(const ScanParams& p, const uint32_t (&r)[32], int q,
                                           float tau, int64_t row0, int rows_valid, int gidx,
-                                          const StagePtr& st) {
+                                          uint2* seg, int& cnt) {
   // r[i] = score(query q, corpus row row0 + i); rows_valid = number of i with row0+i < N (<=32)
   if (MODE == SCAN_DUMP) {
     if (q < p.Q) {
@@ -160,17 +79,23 @@ __device__ __forceinline__ void epi_chunk(const ScanParams& p, const uint32_t (&
         if (i < rows_valid) m = fmaxf(m, __uint_as_float(r[i]));
     }
     p.gmax[(size_t)q * p.gstride + gidx] = m;
-  } else {  // SCAN_FILTER (executed convergently by the whole warp)
+  } else {  // SCAN_FILTER
+    // per-lane test of 8 scores at a time (3-input max tree): ~0.6 instructions per score on the
+    // common path.  A lane with a hit walks its 8 values and appends to ITS query's private
+    // segment: one 8-byte store and a register increment, no atomics.
 #pragma unroll
     for (int s = 0; s < 32; s += 8) {
       const float a = fmax3(__uint_as_float(r[s]), __uint_as_float(r[s + 1]), __uint_as_float(r[s + 2]));
       const float b = fmax3(__uint_as_float(r[s + 3]), __uint_as_float(r[s + 4]), __uint_as_float(r[s + 5]));
       const float m = fmax3(a, b, fmaxf(__uint_as_float(r[s + 6]), __uint_as_float(r[s + 7])));
-      if (__any_sync(0xffffffffu, m >= tau)) {
-        filter_slow8(&p, st.base, st.hdr, tau, (uint32_t)(row0 + s), rows_valid - s,
-                     __uint_as_float(r[s]), __uint_as_float(r[s + 1]), __uint_as_float(r[s + 2]),
-                     __uint_as_float(r[s + 3]), __uint_as_float(r[s + 4]), __uint_as_float(r[s + 5]),
-                     __uint_as_float(r[s + 6]), __uint_as_float(r[s + 7]));
+      if (m >= tau) {
+#pragma unroll
+        for (int i = s; i < s + 8; ++i) {
+          if (__uint_as_float(r[i]) >= tau && i < rows_valid) {
+            if (cnt < p.cap_seg) seg[cnt] = make_uint2(r[i], (uint32_t)(row0 + i));
+            ++cnt;
+          }
+        }
       }
     }
   }
@@ -179,7 +104,7 @@ __device__ __forceinline__ void epi_chunk(const ScanParams& p, const uint32_t (&
 template <int MQ, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX,
-               const __grid_constant__ ScanParams p) {
+               const ScanParams p) {
   using Cfg = ScanCfg<MQ>;
   constexpr int NS = Cfg::NS, NB = Cfg::NB;
   extern __shared__ uint8_t smem_raw[];
@@ -312,20 +237,16 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     constexpr int NCH = (MQ == 2) ? 4 : 2;  // 32-column chunks per tile for this warp
     int tb = 0;
     uint32_t tph = 0;
-    StagePtr st;
-    st.base = smem + Cfg::STAGE_OFF + e * kStageBytes;
-    st.hdr = reinterpret_cast<int*>(smem + Cfg::STAGE_OFF + 8 * kStageBytes) + e * 2;
-    if (lane == 0) { st.hdr[0] = 0; st.hdr[1] = 0; }
-    __syncwarp();
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int split = u / p.QG, qg = u % p.QG;
       const int j0 = (int)((int64_t)split * p.tile_count / p.splits);
       const int j1 = (int)((int64_t)(split + 1) * p.tile_count / p.splits);
       const int q = (qg * MQ + h) * kQBlock + quarter * 32 + lane;
-      if (MODE == SCAN_FILTER) {
-        if (lane == 0) st.hdr[1] = (qg * MQ + h) * kQBlock + quarter * 32;
-        __syncwarp();
-      }
+      // this warp's private candidate segment for (query q, split[, column half g])
+      const int segi = (MQ == 2) ? split : split * 2 + g;
+      uint2* seg = nullptr;
+      int cnt = 0;
+      if (MODE == SCAN_FILTER) seg = p.cand + ((size_t)q * p.nseg + segi) * p.cap_seg;
       const bool warp_active = ((qg * MQ + h) * kQBlock + quarter * 32) < p.Q;
       float tau = INFINITY;
       if (MODE == SCAN_FILTER) tau = p.tau[q];
@@ -348,7 +269,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               const int64_t row0 = tile_row0 + col_begin + c * 32;
               const int64_t rv = p.N - row0;
               const int rows_valid = rv >= 32 ? 32 : (rv < 0 ? 0 : (int)rv);
-              epi_chunk<MODE>(p, r0, q, tau, row0, rows_valid, j * 4 + (col_begin >> 5) + c, st);
+              epi_chunk<MODE>(p, r0, q, tau, row0, rows_valid, j * 4 + (col_begin >> 5) + c, seg, cnt);
             }
             tmem_ld_wait_dep(r1);
             if (c + 2 < NCH) {
@@ -363,7 +284,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               const int64_t row0 = tile_row0 + col_begin + (c + 1) * 32;
               const int64_t rv = p.N - row0;
               const int rows_valid = rv >= 32 ? 32 : (rv < 0 ? 0 : (int)rv);
-              epi_chunk<MODE>(p, r1, q, tau, row0, rows_valid, j * 4 + (col_begin >> 5) + c + 1, st);
+              epi_chunk<MODE>(p, r1, q, tau, row0, rows_valid, j * 4 + (col_begin >> 5) + c + 1, seg, cnt);
             }
           }
         } else {
@@ -373,7 +294,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         if (++tb == NB) { tb = 0; tph ^= 1; }
       }
-      if (MODE == SCAN_FILTER) stage_flush(&p, st.base, st.hdr);  // qbase changes with the unit
+      if (MODE == SCAN_FILTER && warp_active) p.cand_count[(size_t)q * p.nseg + segi] = cnt;
     }
   }
   __syncwarp();

@@ -23,6 +23,7 @@ namespace {
 
 constexpr int kSelThreads = 512;
 constexpr int kRescoreMax = 2048;  // rescore window slots
+constexpr int kKeyCap = 4096;      // candidates per query the select kernel can hold
 
 __device__ __forceinline__ uint64_t make_key(float score, uint32_t idx) {
   return ((uint64_t)f2ord(score) << 32) | (uint64_t)(0xFFFFFFFFu - idx);
@@ -59,8 +60,7 @@ __device__ __forceinline__ int next_pow2(int v) {
 // ------------------------------------------------------------- kth_value ---
 __global__ void __launch_bounds__(kSelThreads)
 kth_value_kernel(const float* __restrict__ vals, int64_t T, int64_t ld, int m, float* __restrict__ tau,
-                 int* __restrict__ cand_count, float* __restrict__ cand_score,
-                 uint32_t* __restrict__ cand_idx, int cap) {
+                 int* __restrict__ cand_count, uint2* __restrict__ cand, int cap) {
   __shared__ int hist[256];
   __shared__ uint32_t s_prefix;
   __shared__ int s_rem;
@@ -105,10 +105,7 @@ kth_value_kernel(const float* __restrict__ vals, int64_t T, int64_t ld, int m, f
       const float v = row[i];
       if (v >= t) {
         const int slot = atomicAdd(&s_count, 1);
-        if (slot < cap) {
-          cand_score[(size_t)r * cap + slot] = v;
-          cand_idx[(size_t)r * cap + slot] = (uint32_t)i;
-        }
+        if (slot < cap) cand[(size_t)r * cap + slot] = make_uint2(__float_as_uint(v), (uint32_t)i);
       }
     }
     __syncthreads();
@@ -128,26 +125,49 @@ constexpr int kSel2Threads = 1024;
 __global__ void __launch_bounds__(kSel2Threads)
 select_rescore_kernel(const SelectParams p) {
   extern __shared__ __align__(16) uint8_t sm[];
-  uint64_t* keys = reinterpret_cast<uint64_t*>(sm);                       // [cap]
-  uint64_t* rkeys = keys + p.cap;                                          // [kRescoreMax]
+  uint64_t* keys = reinterpret_cast<uint64_t*>(sm);                       // [kKeyCap]
+  uint64_t* rkeys = keys + kKeyCap;                                        // [kRescoreMax]
   float* qv = reinterpret_cast<float*>(rkeys + kRescoreMax);               // [d]
   __shared__ int hist[256];
   __shared__ uint32_t s_prefix;
   __shared__ int s_rem;
   __shared__ int s_R;
+  __shared__ int s_c, s_over;
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
-  const int c_total = p.cand_count[q];
-  const int c = c_total < p.cap ? c_total : p.cap;
-  for (int i = tid; i < c; i += blockDim.x)
-    keys[i] = make_key(p.cand_score[(size_t)q * p.cap + i], p.cand_idx[(size_t)q * p.cap + i]);
+  if (tid == 0) { s_c = 0; s_over = 0; }
   for (int i = tid; i < p.d; i += blockDim.x) qv[i] = p.q32[(size_t)q * p.d + i];
+  __syncthreads();
+  {
+    // gather this query's candidate segments (one warp per segment) into the key array
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    for (int sgi = warp; sgi < p.nseg; sgi += nwarps) {
+      const int produced = p.cand_count[(size_t)q * p.nseg + sgi];
+      const int n = produced < p.cap_seg ? produced : p.cap_seg;
+      int pos0 = 0;
+      if (lane == 0) {
+        if (produced > p.cap_seg) s_over = 1;
+        pos0 = n > 0 ? atomicAdd(&s_c, n) : 0;
+      }
+      pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+      const uint2* seg = p.cand + ((size_t)q * p.nseg + sgi) * p.cap_seg;
+      for (int i = lane; i < n; i += 32) {
+        if (pos0 + i < kKeyCap) {
+          const uint2 e = seg[i];
+          keys[pos0 + i] = make_key(__uint_as_float(e.x), e.y);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int c_total = s_over ? kKeyCap + 1 : s_c;
+  const int c = s_c < kKeyCap ? s_c : kKeyCap;
 
   const int kk = (int64_t)p.k < p.N ? p.k : (int)p.N;  // results that exist
   const float tau_q = p.tau[q];
   const float E = p.eps * p.qnorm[q] * (*p.maxnorm) * 1.0001f;
   int status = 0;
-  if (c_total > p.cap) status |= B2R_ST_CAND_OVERFLOW;
+  if (c_total > kKeyCap) status |= B2R_ST_CAND_OVERFLOW;
   if (c < kk && tau_q > -INFINITY) status |= B2R_ST_TOO_FEW;
 
   // ---- k-th largest candidate score (rank m = min(kk, c)), radix select on the high word
@@ -318,23 +338,20 @@ topk_merge_kernel(int P, int k, const float* __restrict__ D_all, const int64_t* 
 }  // namespace
 
 int launch_kth_value(const float* vals, int rows, int64_t T, int64_t ld, int m, float* tau,
-                     int* cand_count, float* cand_score, uint32_t* cand_idx, int cap,
-                     cudaStream_t stream) {
+                     int* cand_count, uint2* cand, int cap, cudaStream_t stream) {
   if (rows <= 0) return B2R_OK;
   if (m < 1) m = 1;
-  kth_value_kernel<<<rows, kSelThreads, 0, stream>>>(vals, T, ld, m, tau, cand_count, cand_score,
-                                                     cand_idx, cap);
+  kth_value_kernel<<<rows, kSelThreads, 0, stream>>>(vals, T, ld, m, tau, cand_count, cand, cap);
   B2R_CHECK_LAUNCH("kth_value_kernel");
   return B2R_OK;
 }
 
 int launch_select_rescore(const SelectParams& p, cudaStream_t stream) {
   if (p.Q <= 0) return B2R_OK;
-  if (p.cap < 1 || (p.cap & (p.cap - 1)) != 0 || p.cap > 4096)
-    return fail(B2R_EINVAL, "select: cap must be a power of two <= 4096");
+  if (p.nseg < 1 || p.cap_seg < 1) return fail(B2R_EINVAL, "select: bad candidate segment layout");
   if (p.k > kRescoreMax / 2) return fail(B2R_EUNSUPPORTED, "select: k must be <= 1024");
   if (p.d % 4 != 0) return fail(B2R_EINVAL, "select: d must be a multiple of 4");
-  const size_t smem = (size_t)p.cap * 8 + (size_t)kRescoreMax * 8 + (size_t)p.d * 4;
+  const size_t smem = (size_t)kKeyCap * 8 + (size_t)kRescoreMax * 8 + (size_t)p.d * 4;
   static bool configured[64] = {};
   int dev = 0;
   B2R_CUDA(cudaGetDevice(&dev));
