@@ -51,10 +51,66 @@ __device__ void bitonic_desc(uint64_t* s, int n) {
   }
 }
 
+// Same sort for n == blockDim.x (one key per thread, kept in a register): compare-exchange
+// distances below 32 go through warp shuffles, only distances >= 32 touch shared memory.
+__device__ void bitonic_desc_reg(uint64_t* s, int n) {
+  const int i = threadIdx.x;
+  uint64_t v = s[i];
+  for (int k = 2; k <= n; k <<= 1) {
+    const bool up = (i & k) == 0;
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      uint64_t o;
+      if (j >= 32) {
+        s[i] = v;
+        __syncthreads();
+        o = s[i ^ j];
+        __syncthreads();
+      } else {
+        o = __shfl_xor_sync(0xffffffffu, v, j);
+      }
+      const bool lower = (i & j) == 0;           // this thread holds the lower index of the pair
+      const bool take_max = (lower == up);       // descending run: lower index keeps the larger key
+      const uint64_t mx = v > o ? v : o, mn = v > o ? o : v;
+      v = take_max ? mx : mn;
+    }
+  }
+  s[i] = v;
+  __syncthreads();
+}
+
 __device__ __forceinline__ int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
   return p;
+}
+
+// Warp-parallel search of the histogram bin (scanning from bin 255 down) that holds rank *s_rem:
+// each lane sums 8 bins, a shuffle scan finds the owning lane, which walks its 8 bins.
+// Called by the first warp only; updates *s_rem and *s_prefix.
+__device__ __forceinline__ void radix_pick_bin(const int* hist, int* s_rem, uint32_t* s_prefix,
+                                               uint32_t prefix, int shift) {
+  const int lane = threadIdx.x & 31;
+  int part = 0;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) part += hist[255 - (lane * 8 + b)];
+  int incl = part;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int rem = *s_rem;
+  __syncwarp();
+  if ((incl >= rem) && (incl - part < rem)) {  // exactly one lane
+    int cum = incl - part, b = 0;
+    for (; b < 7; ++b) {
+      const int hb = hist[255 - (lane * 8 + b)];
+      if (cum + hb >= rem) break;
+      cum += hb;
+    }
+    *s_rem = rem - cum;
+    *s_prefix = prefix | ((uint32_t)(255 - (lane * 8 + b)) << shift);
+  }
 }
 
 // ------------------------------------------------------------- kth_value ---
@@ -82,15 +138,7 @@ kth_value_kernel(const float* __restrict__ vals, int64_t T, int64_t ld, int m, f
         if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
       }
       __syncthreads();
-      if (threadIdx.x == 0) {
-        int rem = s_rem, cum = 0, b = 255;
-        for (; b > 0; --b) {
-          if (cum + hist[b] >= rem) break;
-          cum += hist[b];
-        }
-        s_rem = rem - cum;
-        s_prefix = prefix | ((uint32_t)b << shift);
-      }
+      if (threadIdx.x < 32) radix_pick_bin(hist, &s_rem, &s_prefix, prefix, shift);
       __syncthreads();
       prefix = s_prefix;
       mask |= 255u << shift;
@@ -111,6 +159,48 @@ kth_value_kernel(const float* __restrict__ vals, int64_t T, int64_t ld, int m, f
     __syncthreads();
     if (threadIdx.x == 0) cand_count[r] = s_count;
   }
+}
+
+// kth_value for short rows (T <= 4096, the sampled group maxima): the row is read ONCE into
+// registers (coalesced), the four radix passes run on registers + a shared histogram.
+constexpr int kKthSmallThreads = 256;
+constexpr int kKthSmallPer = 16;
+
+__global__ void __launch_bounds__(kKthSmallThreads)
+kth_value_small_kernel(const float* __restrict__ vals, int T, int64_t ld, int m, float* __restrict__ tau) {
+  __shared__ int hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_rem;
+  const int r = blockIdx.x;
+  const float* row = vals + (size_t)r * ld;
+  uint32_t key[kKthSmallPer];
+#pragma unroll
+  for (int u = 0; u < kKthSmallPer; ++u) {
+    const int i = u * kKthSmallThreads + threadIdx.x;
+    key[u] = i < T ? f2ord(row[i]) : 0u;   // padding keys sort below every real value
+  }
+  if (m >= T) {
+    if (threadIdx.x == 0) tau[r] = -INFINITY;
+    return;
+  }
+  uint32_t prefix = 0, mask = 0;
+  if (threadIdx.x == 0) s_rem = m;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kKthSmallPer; ++u) {
+      if (u * kKthSmallThreads < T && (key[u] & mask) == prefix && key[u] != 0u)
+        atomicAdd(&hist[(key[u] >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) radix_pick_bin(hist, &s_rem, &s_prefix, prefix, shift);
+    __syncthreads();
+    prefix = s_prefix;
+    mask |= 255u << shift;
+  }
+  if (threadIdx.x == 0) tau[r] = ord2f(prefix);
 }
 
 // --------------------------------------------------------- select_rescore ---
@@ -139,17 +229,37 @@ select_rescore_kernel(const SelectParams p) {
   for (int i = tid; i < p.d; i += blockDim.x) qv[i] = p.q32[(size_t)q * p.d + i];
   __syncthreads();
   {
-    // gather this query's candidate segments (one warp per segment) into the key array
-    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    for (int sgi = warp; sgi < p.nseg; sgi += nwarps) {
+    // gather this query's candidate segments into the key array.  Segment counts are read with
+    // one coalesced load, offsets come from a block-wide exclusive scan (shared memory), then
+    // every (segment, lane) pair copies its entries, so all the segment reads are in flight at
+    // once instead of one latency per segment.
+    int* soff = reinterpret_cast<int*>(rkeys);   // [nseg + 1] scratch (rkeys is free until later)
+    for (int sgi = tid; sgi < p.nseg; sgi += blockDim.x) {
       const int produced = p.cand_count[(size_t)q * p.nseg + sgi];
-      const int n = produced < p.cap_seg ? produced : p.cap_seg;
-      int pos0 = 0;
-      if (lane == 0) {
-        if (produced > p.cap_seg) s_over = 1;
-        pos0 = n > 0 ? atomicAdd(&s_c, n) : 0;
+      if (produced > p.cap_seg) s_over = 1;
+      soff[sgi + 1] = produced < p.cap_seg ? produced : p.cap_seg;
+    }
+    if (tid == 0) soff[0] = 0;
+    __syncthreads();
+    if (tid < 32) {  // warp scan over nseg (<= 4096) counts, 32 at a time
+      int carry = 0;
+      for (int b = 0; b < p.nseg; b += 32) {
+        const int idx = b + tid;
+        int v = idx < p.nseg ? soff[idx + 1] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, v, o);
+          if (tid >= o) v += t;
+        }
+        if (idx < p.nseg) soff[idx + 1] = v + carry;
+        carry += __shfl_sync(0xffffffffu, v, 31);
       }
-      pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+      if (tid == 0) s_c = carry;
+    }
+    __syncthreads();
+    const int lane = tid & 31;
+    for (int sgi = tid >> 5; sgi < p.nseg; sgi += (blockDim.x >> 5)) {
+      const int pos0 = soff[sgi], n = soff[sgi + 1] - pos0;
       const uint2* seg = p.cand + ((size_t)q * p.nseg + sgi) * p.cap_seg;
       for (int i = lane; i < n; i += 32) {
         if (pos0 + i < kKeyCap) {
@@ -185,15 +295,7 @@ select_rescore_kernel(const SelectParams p) {
         if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
       }
       __syncthreads();
-      if (tid == 0) {
-        int rem = s_rem, cum = 0, b = 255;
-        for (; b > 0; --b) {
-          if (cum + hist[b] >= rem) break;
-          cum += hist[b];
-        }
-        s_rem = rem - cum;
-        s_prefix = prefix | ((uint32_t)b << shift);
-      }
+      if (tid < 32) radix_pick_bin(hist, &s_rem, &s_prefix, prefix, shift);
       __syncthreads();
       prefix = s_prefix;
       mask |= 255u << shift;
@@ -268,7 +370,8 @@ select_rescore_kernel(const SelectParams p) {
   const int R2 = next_pow2(R > 1 ? R : 1);
   for (int i = R + tid; i < R2; i += blockDim.x) rkeys[i] = 0;
   __syncthreads();
-  bitonic_desc(rkeys, R2);
+  if (R2 == (int)blockDim.x) bitonic_desc_reg(rkeys, R2);
+  else bitonic_desc(rkeys, R2);
 
   const int avail = R < kk ? R : kk;
   for (int j = tid; j < p.k; j += blockDim.x) {
@@ -341,6 +444,11 @@ int launch_kth_value(const float* vals, int rows, int64_t T, int64_t ld, int m, 
                      int* cand_count, uint2* cand, int cap, cudaStream_t stream) {
   if (rows <= 0) return B2R_OK;
   if (m < 1) m = 1;
+  if (!cand_count && T <= kKthSmallThreads * kKthSmallPer) {
+    kth_value_small_kernel<<<rows, kKthSmallThreads, 0, stream>>>(vals, (int)T, ld, m, tau);
+    B2R_CHECK_LAUNCH("kth_value_small_kernel");
+    return B2R_OK;
+  }
   kth_value_kernel<<<rows, kSelThreads, 0, stream>>>(vals, T, ld, m, tau, cand_count, cand, cap);
   B2R_CHECK_LAUNCH("kth_value_kernel");
   return B2R_OK;
