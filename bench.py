@@ -135,8 +135,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    # bounded workload: the full 1M-row corpus, a 256-query sample of the batch per step
-    n = CORPUS_1GPU
+    torch.set_num_threads(os.cpu_count() or 1)   # torchrun pins OMP_NUM_THREADS=1; use every host core
+    world = max(args.gpus, int(os.environ.get("WORLD_SIZE", "1")))
+    total_rows = args.corpus_rows or (CORPUS_1GPU if world == 1 else CORPUS_MULTI)
+    # bounded sample of the workload: a 256-query slice of the batch against (at most) a 1M-row slice of
+    # the corpus per step; throughput is scaled to the whole corpus (a flat scan is linear in rows)
+    n = min(total_rows, CORPUS_1GPU)
+    scale = n / total_rows
     sample_q = min(args.batch, 256)
     x = make_host_corpus(n)
     search = cpu_search_fn(x, list(range(n)))
@@ -148,16 +153,19 @@ def run_reference(args):
     for _ in range(args.steps):
         search(q, K_TOP)
     dt = time.perf_counter() - t0
-    val = args.steps * sample_q / dt
+    val = args.steps * sample_q / dt * scale
     cores = torch.get_num_threads()
-    sample = f"{sample_q} of {args.batch} queries per step vs the full {n}x{D} corpus, top-{K_TOP}"
+    sample = (f"{sample_q} of {args.batch} queries per step vs a {n}-row slice of the {total_rows}x{D} corpus, "
+              f"top-{K_TOP}" + (f"; queries/s scaled by {scale:g} to the full corpus" if scale != 1 else ""))
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Flat IP top-{K_TOP} over {n}x{D} ads, batch {args.batch} (CPU: {sample})",
-                   "corpus_rows": n, "dim": D, "k": K_TOP, "batch": args.batch},
+        "config": {"workload": (f"Flat IP top-{K_TOP} over {total_rows}x{D} ad corpus, query batch {args.batch}"
+                                + (f", row-sharded over {world} B200 + NCCL all-gather merge" if world > 1
+                                   else ", single B200") + " [CPU reference arm]"),
+                   "corpus_rows": total_rows, "dim": D, "k": K_TOP, "batch": args.batch},
         "cpu_baseline": {"value": val, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "oracle port (torch-CPU sgemm + topk + python id remap); faiss-cpu is not installable here"},
         "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -173,6 +181,7 @@ def run_b200(args):
     import torch.distributed as dist
     from movie_recommender_demo_b200 import _lib
     from movie_recommender_demo_b200.faiss_retrieval import FAISSIndex
+    from movie_recommender_demo_b200.sharded import ShardedFlatIndex, shard_rows
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -189,29 +198,31 @@ def run_b200(args):
     FAISSIndex.verbose = False
 
     total_rows = args.corpus_rows or (CORPUS_1GPU if world == 1 else CORPUS_MULTI)
-    lo_row = rank * total_rows // world
-    hi_row = (rank + 1) * total_rows // world
+    lo_row, hi_row = shard_rows(total_rows, world, rank)
     Q = args.batch
 
     # ---- corpus shard: generated on the device chunk by chunk (seed = 100 + global chunk id), so the same
     #      rows exist for every world size; never materialised on the host
-    index = FAISSIndex(D, 'Flat', device=local_rank)
     t_build = time.time()
+    if world == 1:
+        index = FAISSIndex(D, 'Flat', device=local_rank)   # reference surface: default ids -> device id map
+        flat = index.index
+        sharded = None
+    else:
+        sharded = ShardedFlatIndex(D, total_rows, device=local_rank)
+        flat = sharded.local
+        index = None
     g = torch.Generator(device=dev)
-    first_chunk = lo_row // CHUNK
-    last_chunk = (hi_row - 1) // CHUNK
-    for c in range(first_chunk, last_chunk + 1):
+    for c in range(lo_row // CHUNK, (hi_row - 1) // CHUNK + 1):
         g.manual_seed(100 + c)
         rows = torch.randn((CHUNK, D), generator=g, device=dev)
         a = max(lo_row, c * CHUNK) - c * CHUNK
         b = min(hi_row, (c + 1) * CHUNK) - c * CHUNK
         if world == 1:
-            index.add(rows[a:b])                       # reference surface: default ids -> device id map
+            index.add(rows[a:b])
         else:
-            index.index.add(rows[a:b], normalize=True)  # shard: labels = base + local row
+            sharded.add_local(rows[a:b], normalize=True)
         del rows
-    if world > 1:
-        index.index.set_label_base(lo_row)
     torch.cuda.synchronize()
     t_build = time.time() - t_build
 
@@ -222,21 +233,11 @@ def run_b200(args):
     q_dev = q_host.to(dev)
     stream_ptr = lambda: int(torch.cuda.current_stream(dev).cuda_stream)  # noqa: E731
 
-    if world > 1:
-        D_all = torch.empty((world, Q, K_TOP), dtype=torch.float32, device=dev)
-        I_all = torch.empty((world, Q, K_TOP), dtype=torch.int64, device=dev)
-        D_out = torch.empty((Q, K_TOP), dtype=torch.float32, device=dev)
-        I_out = torch.empty((Q, K_TOP), dtype=torch.int64, device=dev)
-
     def device_step(queries):
-        Dl, Il, st, _ = index.index.search_device(queries, K_TOP, normalize=True)
         if world == 1:
+            Dl, Il, st, _ = flat.search_device(queries, K_TOP, normalize=True)
             return Dl, Il, st
-        dist.all_gather_into_tensor(D_all, Dl)
-        dist.all_gather_into_tensor(I_all, Il)
-        _lib.check(lib.b2r_topk_merge(world, Q, K_TOP, D_all.data_ptr(), I_all.data_ptr(), D_out.data_ptr(),
-                                      I_out.data_ptr(), 1, stream_ptr()))
-        return D_out, I_out, st
+        return sharded.search_device(queries, K_TOP, normalize=True)   # local scan + all-gather + merge
 
     def e2e_step():
         if world == 1:
@@ -285,16 +286,16 @@ def run_b200(args):
     value = args.steps * Q / (ms_total / 1e3)
 
     # ---- roofline: the filter-scan kernel alone, CUDA events around each launch on its stream
-    index.index.set_param("profile", args.steps)
+    flat.set_param("profile", args.steps)
     barrier()
     w0 = time.time()
     for _ in range(args.steps):
         device_step(q_dev)
     barrier()
     windows.append((w0, time.time()))
-    scan_ms = index.index.get_param("scan_ms_avg")
+    scan_ms = flat.get_param("scan_ms_avg")
     scan_ms = max_over_ranks(scan_ms)
-    index.index.set_param("profile", 0)
+    flat.set_param("profile", 0)
     shard_rows = hi_row - lo_row
     if Q >= 256:
         flops = 2.0 * Q * shard_rows * D
