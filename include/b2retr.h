@@ -136,6 +136,10 @@ int b2r_index_import_codebooks(b2r_index* h, const float* codebooks_host);
 /* Inverted-list sizes (int64 [nlist], host) — for oracle cross-checks. */
 int b2r_index_list_sizes(const b2r_index* h, int64_t* sizes_host);
 
+/* Insertion label of each STORED row [row0,row0+n) (int64, device): identity for FLAT; IVF
+ * keeps rows sorted by inverted list, so label != storage position there. */
+int b2r_index_get_labels(const b2r_index* h, int64_t row0, int64_t n, int64_t* out, void* stream);
+
 /* Copy stored fp32 master rows [row0,row0+n) to a device buffer (save path,
  * replaces what faiss.write_index serialises, faiss_retrieval.py:203-206). */
 int b2r_index_get_vectors(const b2r_index* h, int64_t row0, int64_t n, float* out, void* stream);

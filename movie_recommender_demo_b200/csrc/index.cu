@@ -12,6 +12,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include <mutex>
 #include <vector>
 
@@ -32,44 +34,7 @@ int fail(int code, const std::string& msg) {
 
 using namespace b2r;
 
-struct b2r_index {
-  int kind = 0, d = 0, nlist = 0, pq_m = 0, pq_bits = 0, metric = 0, device = 0;
-  int num_sms = 148;
-  int64_t ntotal = 0, capacity = 0;
-  float* x32 = nullptr;          // [capacity, d] fp32 master rows
-  __nv_bfloat16* x16 = nullptr;  // [capacity, d] bf16 scan rows
-  float* maxnorm = nullptr;      // device scalar: max stored row norm
-  int64_t* ids = nullptr;        // optional id map [n_ids]
-  int64_t n_ids = 0;
-  int64_t label_base = 0;
-  CUtensorMap tmX;
-  bool trained = true;
-  // tunables
-  double eps = 0.00390625 * 1.02;  // 2^-8 (two bf16 roundings per product), 2% slack
-  double cand_factor = 4.0;
-  int cand_cap = 4096;
-  int rescore = 1;
-  int force_path = 0;  // 0 auto, 1 dense, 2 filter (tests)
-  int64_t dense_budget = (int64_t)1 << 30;  // bytes of dumped scores per query chunk
-  // optional CUDA-event timing of the dominant (filter scan) kernel, for bench.py's roofline
-  int profile = 0;
-  std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
-  size_t prof_used = 0;
-};
-
 namespace {
-
-struct DeviceGuard {
-  int prev = -1;
-  bool ok = true;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
-    if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
 
 // ---- search plan: path + workspace layout for one query chunk ----------------
 struct Plan {
@@ -243,8 +208,10 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
     dp.dump = aux;
     dp.ld = pl.dump_ld;
     if ((rc = launch_scan(SCAN_DUMP, MQ, tmQ, h->tmX, dp, h->num_sms, stream))) return rc;
-    const int m = (int64_t)pl.c_target < h->ntotal ? pl.c_target : (int)h->ntotal;
-    if ((rc = launch_kth_value(aux, q, h->ntotal, pl.dump_ld, m, tau, count, cand, pl.cap_seg, stream)))
+    // exact k-th bf16 score per query, threshold = k-th - 2E: the candidates ARE the provable window
+    const int m = (int64_t)k < h->ntotal ? k : (int)h->ntotal;
+    if ((rc = launch_kth_value(aux, q, h->ntotal, pl.dump_ld, m, tau, count, cand, pl.cap_seg,
+                               h->rescore ? qnorm : nullptr, h->maxnorm, (float)h->eps, stream)))
       return rc;
     sel_nseg = 1;
     sel_cap_seg = pl.cap_seg;
@@ -257,7 +224,8 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
     gp.gmax = aux;
     gp.gstride = (int)pl.gstride;
     if ((rc = launch_scan(SCAN_GMAX, MQ, tmQ, h->tmX, gp, h->num_sms, stream))) return rc;
-    if ((rc = launch_kth_value(aux, q, pl.gstride, pl.gstride, pl.m_rank, tau, nullptr, nullptr, 0, stream)))
+    if ((rc = launch_kth_value(aux, q, pl.gstride, pl.gstride, pl.m_rank, tau, nullptr, nullptr, 0, nullptr, nullptr,
+                               0.f, stream)))
       return rc;
   }
   if (tau_in || !pl.dense) {
@@ -297,22 +265,12 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
 
 }  // namespace
 
-// =============================================================== C ABI =====
-extern "C" {
+namespace b2r {
 
-int b2r_version(void) { return B2R_VERSION; }
-const char* b2r_last_error(void) { return t_error.c_str(); }
-int64_t b2r_debug_launch_count(void) { return (int64_t)g_launches.load(); }
-
-int b2r_index_create(b2r_index** out, int kind, int d, int nlist, int pq_m, int pq_bits, int metric,
-                     int device) {
-  if (!out) return fail(B2R_EINVAL, "index_create: out is NULL");
+int flat_create(b2r_index** out, int d, int device) {
   *out = nullptr;
-  if (kind != B2R_KIND_FLAT)
-    return fail(B2R_EUNSUPPORTED, "index_create: only B2R_KIND_FLAT is implemented in this build");
   if (d < 64 || d > 256 || d % 64 != 0)
     return fail(B2R_EINVAL, "index_create: d must be a multiple of 64 in [64, 256]");
-  if (metric != B2R_METRIC_IP) return fail(B2R_EUNSUPPORTED, "index_create: flat index supports inner product only");
   int ndev = 0;
   B2R_CUDA(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(B2R_EINVAL, "index_create: bad device ordinal");
@@ -323,12 +281,9 @@ int b2r_index_create(b2r_index** out, int kind, int d, int nlist, int pq_m, int 
                                       std::to_string(prop.minor) + ", this library is sm_100a only");
   DeviceGuard g(device);
   b2r_index* h = new b2r_index();
-  h->kind = kind;
+  h->kind = B2R_KIND_FLAT;
   h->d = d;
-  h->nlist = nlist;
-  h->pq_m = pq_m;
-  h->pq_bits = pq_bits;
-  h->metric = metric;
+  h->metric = B2R_METRIC_IP;
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   if (cudaMalloc(&h->maxnorm, 256) != cudaSuccess) {
@@ -341,6 +296,103 @@ int b2r_index_create(b2r_index** out, int kind, int d, int nlist, int pq_m, int 
   return B2R_OK;
 }
 
+int flat_add(b2r_index* h, int64_t n, const float* x, int normalize, cudaStream_t stream) {
+  if (n == 0) return B2R_OK;
+  if (h->ntotal + n > 0x7FFFFF00ll) return fail(B2R_EUNSUPPORTED, "index_add: more than 2^31 rows per shard");
+  int rc = ensure_capacity(h, h->ntotal + n, stream);
+  if (rc) return rc;
+  rc = launch_ingest(x, n, h->d, normalize, h->x32 + (size_t)h->ntotal * h->d,
+                     h->x16 + (size_t)h->ntotal * h->d, h->maxnorm, stream);
+  if (rc) return rc;
+  h->ntotal += n;
+  return make_tmap_bf16_rows(&h->tmX, h->x16, h->ntotal, h->d);
+}
+
+size_t flat_search_workspace(const b2r_index* h, int q, int k) {
+  if (!h || q <= 0 || k <= 0) return 0;
+  const Plan a = make_plan(h, q, k, false);
+  const Plan b = make_plan(h, q, k, true);
+  return a.total > b.total ? a.total : b.total;
+}
+
+int flat_search(b2r_index* h, int q, const float* queries, int normalize, int k, float* D, int64_t* I,
+                int32_t* status, float* tau_retry, const float* tau_in, void* workspace, size_t ws_bytes,
+                cudaStream_t stream) {
+  const Plan pl = make_plan(h, q, k, tau_in != nullptr);
+  if (!workspace || ws_bytes < pl.total)
+    return fail(B2R_ENOMEM, "index_search: workspace too small (need " + std::to_string(pl.total) + " bytes)");
+  if (((uintptr_t)workspace & 255) != 0) return fail(B2R_EINVAL, "index_search: workspace must be 256-byte aligned");
+  if (h->ntotal == 0) {
+    // empty index: every slot is empty (faiss returns -1 labels)
+    int rc = launch_fill_f32(D, (int64_t)q * k, -3.4028234663852886e38f, stream);
+    if (rc) return rc;
+    B2R_CUDA(cudaMemsetAsync(I, 0xFF, (size_t)q * k * 8, stream));
+    if (status) B2R_CUDA(cudaMemsetAsync(status, 0, (size_t)q * 4, stream));
+    if (tau_retry) B2R_CUDA(cudaMemsetAsync(tau_retry, 0, (size_t)q * 4, stream));
+    return B2R_OK;
+  }
+  for (int q0 = 0; q0 < q; q0 += pl.chunk) {
+    const int qc = (q - q0) < pl.chunk ? (q - q0) : pl.chunk;
+    int rc = flat_search_chunk(h, pl, qc, queries + (size_t)q0 * h->d, normalize, k, D + (size_t)q0 * k,
+                               I + (size_t)q0 * k, status ? status + q0 : nullptr,
+                               tau_retry ? tau_retry + q0 : nullptr, tau_in ? tau_in + q0 : nullptr,
+                               reinterpret_cast<uint8_t*>(workspace), stream);
+    if (rc) return rc;
+  }
+  return B2R_OK;
+}
+
+}  // namespace b2r
+
+// =============================================================== C ABI =====
+extern "C" {
+
+int b2r_version(void) { return B2R_VERSION; }
+const char* b2r_last_error(void) { return t_error.c_str(); }
+int64_t b2r_debug_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int b2r_index_create(b2r_index** out, int kind, int d, int nlist, int pq_m, int pq_bits, int metric,
+                     int device) {
+  if (!out) return fail(B2R_EINVAL, "index_create: out is NULL");
+  *out = nullptr;
+  if (kind != B2R_KIND_FLAT && kind != B2R_KIND_IVF_FLAT && kind != B2R_KIND_IVF_PQ)
+    return fail(B2R_EINVAL, "index_create: unknown index kind");
+  if (kind == B2R_KIND_FLAT && metric != B2R_METRIC_IP)
+    return fail(B2R_EUNSUPPORTED, "index_create: the flat index supports inner product only");
+  if (kind == B2R_KIND_IVF_FLAT && metric != B2R_METRIC_IP)
+    return fail(B2R_EUNSUPPORTED, "index_create: IVF-Flat supports inner product only");
+  if (kind == B2R_KIND_IVF_PQ && metric != B2R_METRIC_L2)
+    return fail(B2R_EUNSUPPORTED, "index_create: IVF-PQ supports the L2 metric only (the reference's default)");
+  b2r_index* h = nullptr;
+  int rc = flat_create(&h, d, device);
+  if (rc) return rc;
+  h->kind = kind;
+  h->metric = metric;
+  if (kind != B2R_KIND_FLAT) {
+    if (nlist < 1 || nlist > 65536) {
+      b2r_index_destroy(h);
+      return fail(B2R_EINVAL, "index_create: nlist must be in [1, 65536]");
+    }
+    h->nlist = nlist;
+    h->trained = false;
+    rc = flat_create(&h->quantizer, d, device);
+    if (rc) {
+      b2r_index_destroy(h);
+      return rc;
+    }
+    if (kind == B2R_KIND_IVF_PQ) {
+      if (pq_bits != 8 || pq_m < 1 || d % pq_m != 0 || (d / pq_m) % 4 != 0 || pq_m > 64) {
+        b2r_index_destroy(h);
+        return fail(B2R_EINVAL, "index_create: IVF-PQ needs pq_bits == 8, pq_m <= 64 dividing d with (d/pq_m) % 4 == 0");
+      }
+      h->pq_m = pq_m;
+      h->pq_bits = pq_bits;
+    }
+  }
+  *out = h;
+  return B2R_OK;
+}
+
 int b2r_index_destroy(b2r_index* h) {
   if (!h) return B2R_OK;
   DeviceGuard g(h->device);
@@ -349,6 +401,8 @@ int b2r_index_destroy(b2r_index* h) {
   cudaFree(h->maxnorm);
   cudaFree(h->ids);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  ivf_free(h);
+  if (h->quantizer) b2r_index_destroy(h->quantizer);
   delete h;
   return B2R_OK;
 }
@@ -358,6 +412,8 @@ int b2r_index_reset(b2r_index* h) {
   DeviceGuard g(h->device);
   h->ntotal = 0;
   B2R_CUDA(cudaMemset(h->maxnorm, 0, 256));
+  std::fill(h->list_sizes_host.begin(), h->list_sizes_host.end(), 0);
+  if (h->list_off) B2R_CUDA(cudaMemset(h->list_off, 0, (size_t)(h->nlist + 1) * 8));
   return B2R_OK;
 }
 
@@ -365,25 +421,21 @@ int64_t b2r_index_ntotal(const b2r_index* h) { return h ? h->ntotal : 0; }
 int b2r_index_is_trained(const b2r_index* h) { return h ? (h->trained ? 1 : 0) : 0; }
 
 int b2r_index_train(b2r_index* h, int64_t n, const float* x, uint64_t seed, void* stream) {
-  (void)n; (void)x; (void)seed; (void)stream;
   if (!h) return fail(B2R_EINVAL, "index_train: NULL handle");
-  return B2R_OK;  // flat: always trained (faiss IndexFlat::train is a no-op)
+  if (h->kind == B2R_KIND_FLAT || h->trained) return B2R_OK;  // faiss: IndexFlat::train is a no-op
+  if (n < 1 || !x) return fail(B2R_EINVAL, "index_train: no training vectors");
+  DeviceGuard g(h->device);
+  return ivf_train(h, n, x, seed, (cudaStream_t)stream);
 }
 
 int b2r_index_add(b2r_index* h, int64_t n, const float* x, int normalize, void* stream_) {
   if (!h) return fail(B2R_EINVAL, "index_add: NULL handle");
   if (n < 0 || (n > 0 && !x)) return fail(B2R_EINVAL, "index_add: bad arguments");
   if (n == 0) return B2R_OK;
-  if (h->ntotal + n > 0x7FFFFF00ll) return fail(B2R_EUNSUPPORTED, "index_add: more than 2^31 rows per shard");
   DeviceGuard g(h->device);
-  cudaStream_t stream = (cudaStream_t)stream_;
-  int rc = ensure_capacity(h, h->ntotal + n, stream);
-  if (rc) return rc;
-  rc = launch_ingest(x, n, h->d, normalize, h->x32 + (size_t)h->ntotal * h->d,
-                     h->x16 + (size_t)h->ntotal * h->d, h->maxnorm, stream);
-  if (rc) return rc;
-  h->ntotal += n;
-  return make_tmap_bf16_rows(&h->tmX, h->x16, h->ntotal, h->d);
+  if (h->kind == B2R_KIND_FLAT) return flat_add(h, n, x, normalize, (cudaStream_t)stream_);
+  if (!h->trained) return fail(B2R_ESTATE, "index_add: index is not trained");
+  return ivf_add(h, n, x, normalize, (cudaStream_t)stream_);
 }
 
 int b2r_index_set_ids(b2r_index* h, int64_t n, const int64_t* ids, void* stream_) {
@@ -473,18 +525,14 @@ double b2r_index_get_param(const b2r_index* h, const char* name) {
 }
 
 size_t b2r_index_search_workspace(const b2r_index* h, int q, int k, int nprobe) {
-  (void)nprobe;
   if (!h || q <= 0 || k <= 0) return 0;
-  // sized for either mode (with or without caller thresholds)
-  const Plan a = make_plan(h, q, k, false);
-  const Plan b = make_plan(h, q, k, true);
-  return a.total > b.total ? a.total : b.total;
+  if (h->kind == B2R_KIND_FLAT) return flat_search_workspace(h, q, k);
+  return ivf_search_workspace(h, q, k, nprobe);
 }
 
 int b2r_index_search(b2r_index* h, int q, const float* queries, int normalize, int k, int nprobe,
                      float* D, int64_t* I, int32_t* status, float* tau_retry, const float* tau_in,
                      void* workspace, size_t ws_bytes, void* stream_) {
-  (void)nprobe;
   if (!h) return fail(B2R_EINVAL, "index_search: NULL handle");
   if (q < 0 || k < 1 || (q > 0 && (!queries || !D || !I))) return fail(B2R_EINVAL, "index_search: bad arguments");
   if (k > 1024) return fail(B2R_EUNSUPPORTED, "index_search: k must be <= 1024");
@@ -492,28 +540,11 @@ int b2r_index_search(b2r_index* h, int q, const float* queries, int normalize, i
   if (!h->trained) return fail(B2R_ESTATE, "index_search: index is not trained");
   DeviceGuard g(h->device);
   cudaStream_t stream = (cudaStream_t)stream_;
-  const Plan pl = make_plan(h, q, k, tau_in != nullptr);
-  if (!workspace || ws_bytes < pl.total)
-    return fail(B2R_ENOMEM, "index_search: workspace too small (need " + std::to_string(pl.total) + " bytes)");
-  if (((uintptr_t)workspace & 255) != 0) return fail(B2R_EINVAL, "index_search: workspace must be 256-byte aligned");
-  if (h->ntotal == 0) {
-    // empty index: every slot is empty (faiss returns -1 labels)
-    int rc = launch_fill_f32(D, (int64_t)q * k, -3.4028234663852886e38f, stream);
-    if (rc) return rc;
-    B2R_CUDA(cudaMemsetAsync(I, 0xFF, (size_t)q * k * 8, stream));
-    if (status) B2R_CUDA(cudaMemsetAsync(status, 0, (size_t)q * 4, stream));
-    if (tau_retry) B2R_CUDA(cudaMemsetAsync(tau_retry, 0, (size_t)q * 4, stream));
-    return B2R_OK;
-  }
-  for (int q0 = 0; q0 < q; q0 += pl.chunk) {
-    const int qc = (q - q0) < pl.chunk ? (q - q0) : pl.chunk;
-    int rc = flat_search_chunk(h, pl, qc, queries + (size_t)q0 * h->d, normalize, k, D + (size_t)q0 * k,
-                               I + (size_t)q0 * k, status ? status + q0 : nullptr,
-                               tau_retry ? tau_retry + q0 : nullptr, tau_in ? tau_in + q0 : nullptr,
-                               reinterpret_cast<uint8_t*>(workspace), stream);
-    if (rc) return rc;
-  }
-  return B2R_OK;
+  if (h->kind == B2R_KIND_FLAT)
+    return flat_search(h, q, queries, normalize, k, D, I, status, tau_retry, tau_in, workspace, ws_bytes, stream);
+  if (tau_in) return fail(B2R_EUNSUPPORTED, "index_search: caller thresholds apply to the flat index only");
+  if (tau_retry) B2R_CUDA(cudaMemsetAsync(tau_retry, 0, (size_t)q * 4, stream));
+  return ivf_search(h, q, queries, normalize, k, nprobe, D, I, status, workspace, ws_bytes, stream);
 }
 
 int b2r_index_get_vectors(const b2r_index* h, int64_t row0, int64_t n, float* out, void* stream) {
@@ -526,11 +557,6 @@ int b2r_index_get_vectors(const b2r_index* h, int64_t row0, int64_t n, float* ou
   return B2R_OK;
 }
 
-int b2r_index_export_centroids(const b2r_index*, float*) { return fail(B2R_EUNSUPPORTED, "no coarse quantiser on this index kind"); }
-int b2r_index_import_centroids(b2r_index*, const float*) { return fail(B2R_EUNSUPPORTED, "no coarse quantiser on this index kind"); }
-int b2r_index_export_codebooks(const b2r_index*, float*) { return fail(B2R_EUNSUPPORTED, "no PQ codebooks on this index kind"); }
-int b2r_index_import_codebooks(b2r_index*, const float*) { return fail(B2R_EUNSUPPORTED, "no PQ codebooks on this index kind"); }
-int b2r_index_list_sizes(const b2r_index*, int64_t*) { return fail(B2R_EUNSUPPORTED, "no inverted lists on this index kind"); }
 
 // ------------------------------------------------------------------ debug ---
 int b2r_debug_scores_tc(b2r_index* h, int q, const float* queries, int normalize, float* out,

@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <string>
+#include <vector>
 
 #include "../../include/b2retr.h"
 
@@ -34,6 +35,11 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
   } while (0)
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+// Width of the rescore window below the k-th bf16 score: 2E, E = eps * |q| * max|x| bounds
+// |bf16 score - exact score|.  One definition so every kernel computes the identical float.
+__host__ __device__ inline float rescore_margin(float eps, float qnorm, float maxnorm) {
+  return 2.0f * (eps * qnorm * maxnorm * 1.0001f);
+}
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ------------------------------------------------------------ scan kernel ---
@@ -87,8 +93,11 @@ int launch_prep_queries(const float* x, int q, int qpad, int d, int normalize, f
 // ------------------------------------------------------------------ select ---
 // per-row m-th largest of vals[r, 0..T) (ld stride) -> tau[r]; if cand_* given, also
 // appends every (val >= tau[r], column) of row r to the candidate buffers (dense path).
+// With qnorm/maxnorm given (dense path, m = k) the threshold is lowered by the rescore margin:
+// tau = kth - 2E, i.e. exactly the provable rescore window.
 int launch_kth_value(const float* vals, int rows, int64_t T, int64_t ld, int m, float* tau,
-                     int* cand_count, uint2* cand, int cap, cudaStream_t stream);
+                     int* cand_count, uint2* cand, int cap, const float* qnorm, const float* maxnorm,
+                     float eps, cudaStream_t stream);
 struct SelectParams {
   int Q, k, d;
   int nseg, cap_seg;     // candidate segments per query / slots per segment
@@ -102,7 +111,9 @@ struct SelectParams {
   const float* maxnorm;  // device scalar
   float eps;             // relative score error bound
   int rescore;           // 1: fp32 rescore
-  const int64_t* ids;    // optional id map [N]
+  const uint32_t* perm;  // optional stored row -> label (IVF keeps rows sorted by list)
+  const int* scanned;    // optional [Q]: rows actually scanned per query (IVF); results that exist = min(k, scanned)
+  const int64_t* ids;    // optional id map indexed by label
   int64_t label_base;
   float* D;              // [Q,k]
   int64_t* I;            // [Q,k]
@@ -113,4 +124,72 @@ int launch_select_rescore(const SelectParams& p, cudaStream_t stream);
 int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t stream);
 int launch_fill_i32(int* p, int64_t n, int v, cudaStream_t stream);
 
+}  // namespace b2r
+
+struct b2r_index {
+  int kind = 0, d = 0, nlist = 0, pq_m = 0, pq_bits = 0, metric = 0, device = 0;
+  int num_sms = 148;
+  int64_t ntotal = 0, capacity = 0;
+  float* x32 = nullptr;          // [capacity, d] fp32 master rows
+  __nv_bfloat16* x16 = nullptr;  // [capacity, d] bf16 scan rows
+  float* maxnorm = nullptr;      // device scalar: max stored row norm
+  int64_t* ids = nullptr;        // optional id map [n_ids]
+  int64_t n_ids = 0;
+  int64_t label_base = 0;
+  CUtensorMap tmX;
+  bool trained = true;
+  // tunables
+  double eps = 0.00390625 * 1.02;  // 2^-8 (two bf16 roundings per product), 2% slack
+  double cand_factor = 4.0;
+  int cand_cap = 4096;
+  int rescore = 1;
+  int force_path = 0;  // 0 auto, 1 dense, 2 filter (tests)
+  int64_t dense_budget = (int64_t)1 << 30;  // bytes of dumped scores per query chunk
+  // optional CUDA-event timing of the dominant (filter scan) kernel, for bench.py's roofline
+  int profile = 0;
+  std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
+  size_t prof_used = 0;
+  // ---- IVF state (kind != FLAT): rows are stored SORTED BY LIST (x32/x16 above), so every
+  // inverted list is a contiguous row range [list_off[l], list_off[l+1]) the scan can tile.
+  b2r_index* quantizer = nullptr;   // flat IP index over the nlist centroids (faiss: IndexFlatIP quantizer)
+  int64_t* list_off = nullptr;      // device [nlist + 1]
+  int32_t* row_list = nullptr;      // device [capacity] list id of each stored (sorted) row
+  uint32_t* perm = nullptr;         // device [capacity] sorted row -> insertion label
+  std::vector<int64_t> list_sizes_host;  // mirrors list sizes (workspace bounds)
+  // ---- PQ state (kind == IVF_PQ)
+  float* codebooks = nullptr;       // device [pq_m, 256, d/pq_m]
+  uint8_t* codes = nullptr;         // device [capacity, pq_m] (sorted by list)
+  bool pq_trained = false;
+};
+
+
+namespace b2r {
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+    if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+
+// flat search entry shared by the C ABI and the IVF coarse quantiser (index.cu)
+size_t flat_search_workspace(const b2r_index* h, int q, int k);
+int flat_search(b2r_index* h, int q, const float* queries, int normalize, int k, float* D, int64_t* I,
+                int32_t* status, float* tau_retry, const float* tau_in, void* workspace, size_t ws_bytes,
+                cudaStream_t stream);
+int flat_add(b2r_index* h, int64_t n, const float* x, int normalize, cudaStream_t stream);
+int flat_create(b2r_index** out, int d, int device);
+
+// IVF family (ivf.cu)
+int ivf_train(b2r_index* h, int64_t n, const float* x, uint64_t seed, cudaStream_t stream);
+int ivf_add(b2r_index* h, int64_t n, const float* x, int normalize, cudaStream_t stream);
+size_t ivf_search_workspace(const b2r_index* h, int q, int k, int nprobe);
+int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, int nprobe, float* D,
+               int64_t* I, int32_t* status, void* workspace, size_t ws_bytes, cudaStream_t stream);
+void ivf_free(b2r_index* h);
 }  // namespace b2r

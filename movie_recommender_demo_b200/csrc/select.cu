@@ -116,7 +116,8 @@ __device__ __forceinline__ void radix_pick_bin(const int* hist, int* s_rem, uint
 // ------------------------------------------------------------- kth_value ---
 __global__ void __launch_bounds__(kSelThreads)
 kth_value_kernel(const float* __restrict__ vals, int64_t T, int64_t ld, int m, float* __restrict__ tau,
-                 int* __restrict__ cand_count, uint2* __restrict__ cand, int cap) {
+                 int* __restrict__ cand_count, uint2* __restrict__ cand, int cap,
+                 const float* __restrict__ qnorm, const float* __restrict__ maxnorm, float eps) {
   __shared__ int hist[256];
   __shared__ uint32_t s_prefix;
   __shared__ int s_rem;
@@ -144,6 +145,7 @@ kth_value_kernel(const float* __restrict__ vals, int64_t T, int64_t ld, int m, f
       mask |= 255u << shift;
     }
     t = ord2f(prefix);
+    if (qnorm) t -= rescore_margin(eps, qnorm[r], *maxnorm);
   }
   if (threadIdx.x == 0) tau[r] = t;
   if (cand_count) {
@@ -273,9 +275,10 @@ select_rescore_kernel(const SelectParams p) {
   const int c_total = s_over ? kKeyCap + 1 : s_c;
   const int c = s_c < kKeyCap ? s_c : kKeyCap;
 
-  const int kk = (int64_t)p.k < p.N ? p.k : (int)p.N;  // results that exist
+  const int64_t n_avail = p.scanned ? (int64_t)p.scanned[q] : p.N;
+  const int kk = (int64_t)p.k < n_avail ? p.k : (int)n_avail;  // results that exist
   const float tau_q = p.tau[q];
-  const float E = p.eps * p.qnorm[q] * (*p.maxnorm) * 1.0001f;
+  const float margin = rescore_margin(p.eps, p.qnorm[q], *p.maxnorm);
   int status = 0;
   if (c_total > kKeyCap) status |= B2R_ST_CAND_OVERFLOW;
   if (c < kk && tau_q > -INFINITY) status |= B2R_ST_TOO_FEW;
@@ -302,7 +305,7 @@ select_rescore_kernel(const SelectParams p) {
     }
     kth = ord2f(prefix);
   }
-  const float lim = p.rescore ? kth - 2.0f * E : kth;
+  const float lim = p.rescore ? kth - margin : kth;
   if (p.rescore && c >= kk && kk > 0 && tau_q > lim) status |= B2R_ST_NEED_LOWER_TAU;
 
   // ---- compact the rescore window into rkeys (unordered)
@@ -363,8 +366,14 @@ select_rescore_kernel(const SelectParams p) {
       if (lane < 4 && i0 + lane < R) {
         const float a = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
         const uint32_t ix = lane == 0 ? idx[0] : lane == 1 ? idx[1] : lane == 2 ? idx[2] : idx[3];
-        rkeys[i0 + lane] = make_key(a, ix);
+        rkeys[i0 + lane] = make_key(a, p.perm ? p.perm[ix] : ix);   // final order is by label
       }
+    }
+  } else if (p.perm) {
+    __syncthreads();
+    for (int i = tid; i < R; i += blockDim.x) {
+      const uint64_t key = rkeys[i];
+      rkeys[i] = (key & 0xFFFFFFFF00000000ull) | (uint64_t)(0xFFFFFFFFu - p.perm[key_idx(key)]);
     }
   }
   const int R2 = next_pow2(R > 1 ? R : 1);
@@ -441,15 +450,16 @@ topk_merge_kernel(int P, int k, const float* __restrict__ D_all, const int64_t* 
 }  // namespace
 
 int launch_kth_value(const float* vals, int rows, int64_t T, int64_t ld, int m, float* tau,
-                     int* cand_count, uint2* cand, int cap, cudaStream_t stream) {
+                     int* cand_count, uint2* cand, int cap, const float* qnorm, const float* maxnorm,
+                     float eps, cudaStream_t stream) {
   if (rows <= 0) return B2R_OK;
   if (m < 1) m = 1;
-  if (!cand_count && T <= kKthSmallThreads * kKthSmallPer) {
+  if (!cand_count && !qnorm && T <= kKthSmallThreads * kKthSmallPer) {
     kth_value_small_kernel<<<rows, kKthSmallThreads, 0, stream>>>(vals, (int)T, ld, m, tau);
     B2R_CHECK_LAUNCH("kth_value_small_kernel");
     return B2R_OK;
   }
-  kth_value_kernel<<<rows, kSelThreads, 0, stream>>>(vals, T, ld, m, tau, cand_count, cand, cap);
+  kth_value_kernel<<<rows, kSelThreads, 0, stream>>>(vals, T, ld, m, tau, cand_count, cand, cap, qnorm, maxnorm, eps);
   B2R_CHECK_LAUNCH("kth_value_kernel");
   return B2R_OK;
 }

@@ -49,6 +49,7 @@ class _DeviceIndex:
 
     kind = _lib.KIND_FLAT
     metric = METRIC_INNER_PRODUCT
+    _supports_retry = True   # caller-threshold retries exist for the flat scan only
 
     def __init__(self, d: int, *, nlist: int = 0, pq_m: int = 0, pq_bits: int = 0, device=None):
         torch = _lib.require_cuda()
@@ -196,7 +197,7 @@ class _DeviceIndex:
         st = st_h.numpy()
         retries = 0
         prev_tau = None
-        while retries < _MAX_RETRIES:
+        while retries < _MAX_RETRIES and self._supports_retry:
             bad = np.nonzero(st & _RETRY_BITS)[0]
             if bad.size == 0:
                 break
@@ -235,13 +236,23 @@ class _DeviceIndex:
         return h
 
     def reconstruct_n(self, i0: int, n: int):
-        """fp32 master rows [i0, i0+n) as a CUDA tensor (faiss `reconstruct_n`)."""
+        """fp32 master rows of labels [i0, i0+n) as a CUDA tensor (faiss `reconstruct_n`)."""
         torch = self._torch
-        out = torch.empty((n, self.d), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.b2r_index_get_vectors(self._h, int(i0), int(n), out.data_ptr(),
-                                                       _stream_ptr(torch, self.device)))
-        return out
+            sp = _stream_ptr(torch, self.device)
+            if self.kind == _lib.KIND_FLAT:
+                out = torch.empty((n, self.d), dtype=torch.float32, device=self.device)
+                _lib.check(self._lib.b2r_index_get_vectors(self._h, int(i0), int(n), out.data_ptr(), sp))
+                return out
+            # IVF stores rows sorted by list: fetch everything, undo the permutation
+            nt = self.ntotal
+            rows = torch.empty((nt, self.d), dtype=torch.float32, device=self.device)
+            labels = torch.empty(nt, dtype=torch.int64, device=self.device)
+            _lib.check(self._lib.b2r_index_get_vectors(self._h, 0, nt, rows.data_ptr(), sp))
+            _lib.check(self._lib.b2r_index_get_labels(self._h, 0, nt, labels.data_ptr(), sp))
+            out = torch.empty_like(rows)
+            out[labels] = rows
+            return out[i0:i0 + n].contiguous()
 
     # test-only: the full bf16 score matrix via the tcgen05 dump mode / a CUDA-core loop
     def debug_scores(self, x, impl: str = "tc", normalize: bool = False):
