@@ -136,6 +136,13 @@ int b2r_index_import_codebooks(b2r_index* h, const float* codebooks_host);
 /* Inverted-list sizes (int64 [nlist], host) — for oracle cross-checks. */
 int b2r_index_list_sizes(const b2r_index* h, int64_t* sizes_host);
 
+/* PQ codes of the STORED rows [row0,row0+n): uint8 [n, pq_m] device (IVF_PQ only; parity plumbing). */
+int b2r_index_get_codes(const b2r_index* h, int64_t row0, int64_t n, uint8_t* out, void* stream);
+
+/* Restore pre-encoded vectors (load path, replaces faiss.read_index for IVF_PQ): codes uint8
+ * [n, pq_m] and their inverted-list ids int64 [n], both device. */
+int b2r_index_add_codes(b2r_index* h, int64_t n, const uint8_t* codes, const int64_t* list_ids, void* stream);
+
 /* Insertion label of each STORED row [row0,row0+n) (int64, device): identity for FLAT; IVF
  * keeps rows sorted by inverted list, so label != storage position there. */
 int b2r_index_get_labels(const b2r_index* h, int64_t row0, int64_t n, int64_t* out, void* stream);

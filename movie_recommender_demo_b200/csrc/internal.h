@@ -114,6 +114,7 @@ struct SelectParams {
   const uint32_t* perm;  // optional stored row -> label (IVF keeps rows sorted by list)
   const int* scanned;    // optional [Q]: rows actually scanned per query (IVF); results that exist = min(k, scanned)
   const int64_t* ids;    // optional id map indexed by label
+  int negate_out;        // 1: scores are negated distances (L2 paths): D = -score, empty slots +FLT_MAX
   int64_t label_base;
   float* D;              // [Q,k]
   int64_t* I;            // [Q,k]
@@ -192,4 +193,13 @@ size_t ivf_search_workspace(const b2r_index* h, int q, int k, int nprobe);
 int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, int nprobe, float* D,
                int64_t* I, int32_t* status, void* workspace, size_t ws_bytes, cudaStream_t stream);
 void ivf_free(b2r_index* h);
+// product quantiser (ivfpq.cu)
+int pq_residuals(b2r_index* h, int64_t n, const float* x, const int64_t* assign, float* r, cudaStream_t stream);
+int pq_train(b2r_index* h, int64_t n, const float* resid, uint64_t seed, cudaStream_t stream);
+int pq_encode(b2r_index* h, int64_t n, const float* resid, uint8_t* codes, cudaStream_t stream);
+int pq_scatter_codes(const uint8_t* src, const int64_t* dst, int64_t n, int m, const int32_t* list_src,
+                     const int64_t* assign_src, const uint32_t* perm_src, uint32_t label0, uint8_t* ocodes,
+                     int32_t* olist, uint32_t* operm, cudaStream_t stream);
+int pq_scan(b2r_index* h, int npairs, const float* q32, const int64_t* coarse, int nprobe, const int64_t* pair_out,
+            float* scorebuf, cudaStream_t stream);
 }  // namespace b2r

@@ -570,7 +570,7 @@ int set_centroids(b2r_index* h, const float* cent_dev, cudaStream_t stream) {
     B2R_CUDA(cudaMemsetAsync(h->list_off, 0, (size_t)(h->nlist + 1) * 8, stream));
   }
   h->list_sizes_host.assign(h->nlist, 0);
-  h->trained = true;
+  h->trained = (h->kind != B2R_KIND_IVF_PQ) || h->pq_trained;
   return B2R_OK;
 }
 
@@ -636,8 +636,64 @@ int ivf_train(b2r_index* h, int64_t n, const float* x, uint64_t seed, cudaStream
     B2R_CHECK_LAUNCH("kmeans_finalize_kernel");
   }
   if ((rc = set_centroids(h, cent.as<float>(), stream))) return rc;
+  if (h->kind == B2R_KIND_IVF_PQ) {
+    // product quantiser on the residuals of (a prefix of) the same random training sample
+    const int64_t np_train = nt < 65536 ? nt : 65536;
+    DevBuf resid;
+    if ((rc = resid.alloc((size_t)np_train * d * 4))) return rc;
+    if ((rc = quantizer_assign(h, np_train, xt.as<float>(), 0, 1, assign.as<int64_t>(), stream))) return rc;
+    if ((rc = pq_residuals(h, np_train, xt.as<float>(), assign.as<int64_t>(), resid.as<float>(), stream))) return rc;
+    if ((rc = pq_train(h, np_train, resid.as<float>(), seed, stream))) return rc;
+    h->trained = true;
+  }
   B2R_CUDA(cudaStreamSynchronize(stream));
   return B2R_OK;
+}
+
+// merge n new code rows (with their list ids) into the list-sorted code storage
+static int store_codes(b2r_index* h, int64_t n, const uint8_t* codes_new, const int64_t* assign,
+                       const int64_t* new_off, unsigned long long* cursor, cudaStream_t stream) {
+  const int nlist = h->nlist, m = h->pq_m;
+  const int64_t n_old = h->ntotal, n_all = n_old + n;
+  int rc;
+  DevBuf dst_old, dst_new;
+    uint8_t* ncodes = nullptr;
+    int32_t* nlistid = nullptr;
+    uint32_t* nperm = nullptr;
+    const int64_t cap = (int64_t)align_up((size_t)n_all, 1024);
+    if (cudaMalloc(&ncodes, (size_t)cap * m) != cudaSuccess || cudaMalloc(&nlistid, (size_t)cap * 4) != cudaSuccess ||
+        cudaMalloc(&nperm, (size_t)cap * 4) != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(ncodes); cudaFree(nlistid); cudaFree(nperm);
+      return fail(B2R_ENOMEM, "index_add: cudaMalloc of the code storage failed");
+    }
+    if (n_old > 0) {
+      if ((rc = dst_old.alloc((size_t)n_old * 8))) return rc;
+      place_old_rows_kernel<<<(unsigned)ceil_div(n_old, 256), 256, 0, stream>>>(
+          h->list_off, new_off, nlist, n_old, h->row_list, dst_old.as<int64_t>());
+      B2R_CHECK_LAUNCH("place_old_rows_kernel");
+      if ((rc = pq_scatter_codes(h->codes, dst_old.as<int64_t>(), n_old, m, h->row_list, nullptr, h->perm, 0u, ncodes,
+                                 nlistid, nperm, stream)))
+        return rc;
+    }
+    if ((rc = dst_new.alloc((size_t)n * 8))) return rc;
+    place_new_rows_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(
+        assign, n, cursor, dst_new.as<int64_t>());
+    B2R_CHECK_LAUNCH("place_new_rows_kernel");
+    if ((rc = pq_scatter_codes(codes_new, dst_new.as<int64_t>(), n, m, nullptr, assign,
+                               nullptr, (uint32_t)n_old, ncodes, nlistid, nperm, stream)))
+      return rc;
+    B2R_CUDA(cudaMemcpyAsync(h->list_off, new_off, (size_t)(nlist + 1) * 8, cudaMemcpyDeviceToDevice, stream));
+    std::vector<int64_t> off_host(nlist + 1);
+    B2R_CUDA(cudaMemcpyAsync(off_host.data(), new_off, (size_t)(nlist + 1) * 8, cudaMemcpyDeviceToHost, stream));
+    B2R_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(h->codes); cudaFree(h->row_list); cudaFree(h->perm);
+    h->codes = ncodes; h->row_list = nlistid; h->perm = nperm;
+    h->capacity = cap;
+    h->ntotal = n_all;
+    h->list_sizes_host.resize(nlist);
+    for (int l = 0; l < nlist; ++l) h->list_sizes_host[l] = off_host[l + 1] - off_host[l];
+    return B2R_OK;
 }
 
 int ivf_add(b2r_index* h, int64_t n, const float* x, int normalize, cudaStream_t stream) {
@@ -645,11 +701,14 @@ int ivf_add(b2r_index* h, int64_t n, const float* x, int normalize, cudaStream_t
   const int64_t n_old = h->ntotal, n_all = n_old + n;
   if (n_all > 0x7FFFFF00ll) return fail(B2R_EUNSUPPORTED, "index_add: more than 2^31 rows per shard");
   int rc;
-  // 1. normalised fp32 + bf16 copies of the new rows
+  const bool is_pq = h->kind == B2R_KIND_IVF_PQ;
+  // 1. normalised fp32 (+ bf16 scan copy for IVF-Flat) of the new rows
   DevBuf t32, t16, assign, hist, new_off, cursor, dst_old, dst_new;
   if ((rc = t32.alloc((size_t)n * d * 4))) return rc;
-  if ((rc = t16.alloc((size_t)n * d * 2))) return rc;
-  if ((rc = launch_ingest(x, n, d, normalize, t32.as<float>(), t16.as<__nv_bfloat16>(), h->maxnorm, stream))) return rc;
+  if (!is_pq && (rc = t16.alloc((size_t)n * d * 2))) return rc;
+  if ((rc = launch_ingest(x, n, d, normalize, t32.as<float>(), is_pq ? nullptr : t16.as<__nv_bfloat16>(), h->maxnorm,
+                          stream)))
+    return rc;
   // 2. list assignment: exact max-inner-product centroid (faiss quantizer->assign)
   if ((rc = assign.alloc((size_t)n * 8))) return rc;
   if ((rc = quantizer_assign(h, n, t32.as<float>(), 0, 1, assign.as<int64_t>(), stream))) return rc;
@@ -663,6 +722,17 @@ int ivf_add(b2r_index* h, int64_t n, const float* x, int normalize, cudaStream_t
   scan_lists_kernel<<<1, 1024, 0, stream>>>(hist.as<int>(), n_old > 0 ? h->list_off : nullptr, nlist,
                                             new_off.as<int64_t>(), cursor.as<int64_t>());
   B2R_CHECK_LAUNCH("scan_lists_kernel");
+  if (is_pq) {
+    // 4'. IVF-PQ stores only the codes of the residuals
+    const int m = h->pq_m;
+    DevBuf resid, ncodes_tmp;
+    if ((rc = resid.alloc((size_t)n * d * 4))) return rc;
+    if ((rc = ncodes_tmp.alloc((size_t)n * m))) return rc;
+    if ((rc = pq_residuals(h, n, t32.as<float>(), assign.as<int64_t>(), resid.as<float>(), stream))) return rc;
+    if ((rc = pq_encode(h, n, resid.as<float>(), ncodes_tmp.as<uint8_t>(), stream))) return rc;
+    return store_codes(h, n, ncodes_tmp.as<uint8_t>(), assign.as<int64_t>(), new_off.as<int64_t>(),
+                       cursor.as<unsigned long long>(), stream);
+  }
   // 4. new storage, rows scattered to their list positions
   float* n32 = nullptr;
   __nv_bfloat16* n16 = nullptr;
@@ -703,6 +773,22 @@ int ivf_add(b2r_index* h, int64_t n, const float* x, int normalize, cudaStream_t
   h->list_sizes_host.resize(nlist);
   for (int l = 0; l < nlist; ++l) h->list_sizes_host[l] = off_host[l + 1] - off_host[l];
   return make_tmap_bf16_rows(&h->tmX, h->x16, h->ntotal, d);
+}
+
+int ivf_add_codes(b2r_index* h, int64_t n, const uint8_t* codes, const int64_t* list_ids, cudaStream_t stream) {
+  const int nlist = h->nlist;
+  DevBuf hist, new_off, cursor;
+  int rc;
+  if ((rc = hist.alloc((size_t)nlist * 4))) return rc;
+  if ((rc = new_off.alloc((size_t)(nlist + 1) * 8))) return rc;
+  if ((rc = cursor.alloc((size_t)nlist * 8))) return rc;
+  B2R_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)nlist * 4, stream));
+  hist_lists_kernel<<<296, 256, 0, stream>>>(list_ids, n, nlist, hist.as<int>());
+  B2R_CHECK_LAUNCH("hist_lists_kernel");
+  scan_lists_kernel<<<1, 1024, 0, stream>>>(hist.as<int>(), h->ntotal > 0 ? h->list_off : nullptr, nlist,
+                                            new_off.as<int64_t>(), cursor.as<int64_t>());
+  B2R_CHECK_LAUNCH("scan_lists_kernel");
+  return store_codes(h, n, codes, list_ids, new_off.as<int64_t>(), cursor.as<unsigned long long>(), stream);
 }
 
 // ---- search -------------------------------------------------------------------------
@@ -783,7 +869,7 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
   const IvfPlan pl = make_ivf_plan(h, q, k, nprobe);
   if (!workspace || ws_bytes < pl.total)
     return fail(B2R_ENOMEM, "index_search: workspace too small (need " + std::to_string(pl.total) + " bytes)");
-  if (h->kind == B2R_KIND_IVF_PQ) return fail(B2R_EUNSUPPORTED, "index_search: IVF-PQ scan is not built in this revision");
+  const bool is_pq = h->kind == B2R_KIND_IVF_PQ;
   const int d = h->d, np = pl.nprobe;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   static bool configured[64] = {};
@@ -832,6 +918,10 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     pair_runs_kernel<<<(unsigned)ceil_div(qc, 128), 128, 0, stream>>>(coarse, qc, np, h->list_off, pl.smax, pair_out,
                                                                       row_len, listcnt);
     B2R_CHECK_LAUNCH("pair_runs_kernel");
+    if (is_pq) {
+      // ADC scan: one CTA per (query, probed list) pair, LUT in shared memory (ivfpq.cu)
+      if ((rc = pq_scan(h, npairs, q32, coarse, np, pair_out, scorebuf, stream))) return rc;
+    } else {
     scan_lists_kernel<<<1, 1024, 0, stream>>>(listcnt, nullptr, h->nlist, pairoff, cursor);
     B2R_CHECK_LAUNCH("scan_lists_kernel(pairs)");
     scatter_pairs_kernel<<<(unsigned)ceil_div(npairs, 8), 256, 0, stream>>>(
@@ -852,9 +942,10 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     sp.scorebuf = scorebuf;
     ivf_scan_kernel<<<h->num_sms, kIvfThreads, kIvfSmem, stream>>>(tmQ, h->tmX, sp);
     B2R_CHECK_LAUNCH("ivf_scan_kernel");
+    }
     ivf_threshold_kernel<<<qc, kIvfSelThreads, (size_t)np * 16, stream>>>(
         scorebuf, pl.smax, row_len, k, coarse, np, h->list_off, tau, count, cand, pl.cap,
-        h->rescore ? qnorm : nullptr, h->maxnorm, (float)h->eps);
+        (h->rescore && !is_pq) ? qnorm : nullptr, h->maxnorm, (float)h->eps);
     B2R_CHECK_LAUNCH("ivf_threshold_kernel");
     SelectParams sel;
     memset(&sel, 0, sizeof(sel));
@@ -872,7 +963,8 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     sel.x32 = h->x32;
     sel.maxnorm = h->maxnorm;
     sel.eps = (float)h->eps;
-    sel.rescore = h->rescore;
+    sel.rescore = is_pq ? 0 : h->rescore;   // ADC distances are the result (faiss does not re-rank)
+    sel.negate_out = is_pq ? 1 : 0;
     sel.perm = h->perm;
     sel.ids = (h->ids && h->n_ids >= h->ntotal) ? h->ids : nullptr;
     sel.label_base = h->label_base;
@@ -916,6 +1008,16 @@ int b2r_index_import_centroids(b2r_index* h, const float* in) {
   return B2R_OK;
 }
 
+/* Restore pre-encoded vectors (load path): codes uint8 [n, pq_m] and their list ids int64 [n], device. */
+int b2r_index_add_codes(b2r_index* h, int64_t n, const uint8_t* codes, const int64_t* list_ids, void* stream) {
+  if (!h || (n > 0 && (!codes || !list_ids))) return fail(B2R_EINVAL, "add_codes: NULL argument");
+  if (h->kind != B2R_KIND_IVF_PQ) return fail(B2R_EUNSUPPORTED, "add_codes: IVF-PQ only");
+  if (!h->trained) return fail(B2R_ESTATE, "add_codes: index is not trained");
+  if (n <= 0) return B2R_OK;
+  DeviceGuard g(h->device);
+  return ivf_add_codes(h, n, codes, list_ids, (cudaStream_t)stream);
+}
+
 int b2r_index_list_sizes(const b2r_index* h, int64_t* sizes) {
   if (!h || !sizes) return fail(B2R_EINVAL, "list_sizes: NULL argument");
   if (h->kind == B2R_KIND_FLAT) return fail(B2R_EUNSUPPORTED, "no inverted lists on this index kind");
@@ -923,8 +1025,6 @@ int b2r_index_list_sizes(const b2r_index* h, int64_t* sizes) {
   return B2R_OK;
 }
 
-int b2r_index_export_codebooks(const b2r_index*, float*) { return fail(B2R_EUNSUPPORTED, "PQ codebooks: not built in this revision"); }
-int b2r_index_import_codebooks(b2r_index*, const float*) { return fail(B2R_EUNSUPPORTED, "PQ codebooks: not built in this revision"); }
 
 int b2r_index_get_labels(const b2r_index* h, int64_t row0, int64_t n, int64_t* out, void* stream) {
   if (!h || (n > 0 && !out)) return fail(B2R_EINVAL, "get_labels: NULL argument");

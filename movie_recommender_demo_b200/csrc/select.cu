@@ -389,10 +389,10 @@ select_rescore_kernel(const SelectParams p) {
     if (j < avail) {
       const uint64_t key = rkeys[j];
       const uint32_t idx = key_idx(key);
-      dv = key_score(key);
+      dv = p.negate_out ? -key_score(key) : key_score(key);
       iv = p.ids ? p.ids[idx] : (p.label_base + (int64_t)idx);
     } else {
-      dv = -FLT_MAX;
+      dv = p.negate_out ? FLT_MAX : -FLT_MAX;
       iv = (p.ids && p.N > 0) ? p.ids[p.N - 1] : -1;  // reference: id_map[-1] wrap-around
     }
     p.D[(size_t)q * p.k + j] = dv;

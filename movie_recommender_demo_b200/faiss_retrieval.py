@@ -399,11 +399,14 @@ class FAISSIndex:
         Path(filepath).parent.mkdir(parents=True, exist_ok=True)
         state = self.index.state_dict() if hasattr(self.index, "state_dict") else {}
         n = self.index.ntotal
-        vecs = self.index.reconstruct_n(0, n).cpu().numpy() if n else np.zeros((0, self.dimension), np.float32)
+        if n and getattr(self.index, "stores_vectors", True):
+            vecs = self.index.reconstruct_n(0, n).cpu().numpy()
+        else:   # empty, or IVF-PQ (codes travel in `state`)
+            vecs = np.zeros((0, self.dimension), np.float32)
         with open(filepath, "wb") as f:
             f.write(_NATIVE_MAGIC)
             blob = pickle.dumps({"index_type": self.index_type, "dimension": self.dimension,
-                                 "ntotal": n, "state": state}, protocol=4)
+                                 "ntotal": len(vecs), "state": state, "pq_m": self._pq_m}, protocol=4)
             f.write(struct.pack("<Q", len(blob)))
             f.write(blob)
             f.write(vecs.astype(np.float32, copy=False).tobytes())
@@ -427,6 +430,7 @@ class FAISSIndex:
             (blen,) = struct.unpack("<Q", f.read(8))
             head = pickle.loads(f.read(blen))
             vecs = np.frombuffer(f.read(), dtype=np.float32).reshape(head["ntotal"], head["dimension"])
+        self._pq_m = head.get("pq_m", self._pq_m)
         verbose, self.verbose = self.verbose, False
         try:
             self._create_index()

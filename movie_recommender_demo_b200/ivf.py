@@ -67,6 +67,74 @@ class IndexIVFPQ(IndexIVFFlat):
         self.pq_m = int(m)
         super().__init__(d, nlist, device=device, pq_m=m)
 
+    def export_codebooks(self) -> np.ndarray:
+        out = np.empty((self.pq_m, 256, self.d // self.pq_m), dtype=np.float32)
+        _lib.check(self._lib.b2r_index_export_codebooks(self._h, out.ctypes.data))
+        return out
+
+    def import_codebooks(self, codebooks) -> None:
+        cb = np.ascontiguousarray(codebooks, dtype=np.float32)
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._lib.b2r_index_import_codebooks(self._h, cb.ctypes.data))
+
+    def codes_by_label(self) -> np.ndarray:
+        """uint8 [ntotal, m] PQ codes in insertion (label) order."""
+        torch = self._torch
+        n = self.ntotal
+        with torch.cuda.device(self.device):
+            sp = int(torch.cuda.current_stream(self.device).cuda_stream)
+            codes = torch.empty((n, self.pq_m), dtype=torch.uint8, device=self.device)
+            labels = torch.empty(n, dtype=torch.int64, device=self.device)
+            _lib.check(self._lib.b2r_index_get_codes(self._h, 0, n, codes.data_ptr(), sp))
+            _lib.check(self._lib.b2r_index_get_labels(self._h, 0, n, labels.data_ptr(), sp))
+            out = torch.empty_like(codes)
+            out[labels] = codes
+        return out.cpu().numpy()
+
+    def reconstruct_n(self, i0: int, n: int):
+        raise NotImplementedError("IVF-PQ stores codes only")
+
+    def lists_by_label(self) -> np.ndarray:
+        """int64 [ntotal] inverted-list id of every vector, in insertion (label) order."""
+        torch = self._torch
+        n = self.ntotal
+        stored = np.repeat(np.arange(self.nlist, dtype=np.int64), self.list_sizes())   # rows are sorted by list
+        with torch.cuda.device(self.device):
+            labels = torch.empty(n, dtype=torch.int64, device=self.device)
+            _lib.check(self._lib.b2r_index_get_labels(self._h, 0, n, labels.data_ptr(),
+                                                      int(torch.cuda.current_stream(self.device).cuda_stream)))
+        out = np.empty(n, dtype=np.int64)
+        out[labels.cpu().numpy()] = stored
+        return out
+
+    def add_codes(self, codes, lists) -> None:
+        torch = self._torch
+        c = torch.as_tensor(np.ascontiguousarray(codes, dtype=np.uint8)).to(self.device)
+        l = torch.as_tensor(np.ascontiguousarray(lists, dtype=np.int64)).to(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.b2r_index_add_codes(self._h, c.shape[0], c.data_ptr(), l.data_ptr(),
+                                                     int(torch.cuda.current_stream(self.device).cuda_stream)))
+            torch.cuda.current_stream(self.device).synchronize()
+
+    stores_vectors = False
+
+    def state_dict(self) -> dict:
+        if not self.is_trained:
+            return {}
+        st = {"centroids": self.export_centroids(), "codebooks": self.export_codebooks()}
+        if self.ntotal:
+            st["codes"] = self.codes_by_label()
+            st["lists"] = self.lists_by_label()
+        return st
+
+    def load_state_dict(self, state: dict) -> None:
+        if "codebooks" in state:
+            self.import_codebooks(state["codebooks"])
+        if "centroids" in state:
+            self.import_centroids(state["centroids"])
+        if "codes" in state:
+            self.add_codes(state["codes"], state["lists"])
+
 
 def create(owner, kind):
     if kind == 'IVF':

@@ -126,6 +126,7 @@ class OracleFAISSIndex:
         if hasattr(self.index, 'nprobe'):
             self.index.nprobe = self.nprobe
         distances, indices = self.index.search(q, k, extra) if extra else self.index.search(q, k)
+        indices = np.asarray(indices)
         table = np.empty(len(self.id_map), dtype=object)
         table[:] = self.id_map
         ad_ids = np.array(table[indices].tolist())      # id_map[idx]; -1 wraps to the last id (:159-160)
