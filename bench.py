@@ -212,6 +212,8 @@ def run_b200(args):
         sharded = ShardedFlatIndex(D, total_rows, device=local_rank)
         flat = sharded.local
         index = None
+    if args.scan_dtype != "auto":
+        flat.set_param("scan_dtype", {"bf16": 0, "fp16": 1}[args.scan_dtype])
     g = torch.Generator(device=dev)
     for c in range(lo_row // CHUNK, (hi_row - 1) // CHUNK + 1):
         g.manual_seed(100 + c)
@@ -359,13 +361,14 @@ def run_b200(args):
         out = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic",
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "dtype": "f16" if int(flat.get_param("scan_dtype")) == 1 else "bf16", "data": "synthetic",
             "config": {
                 "workload": (f"Flat IP top-{K_TOP} over {total_rows}x{D} ad corpus, query batch {Q}"
                              + (f", row-sharded over {world} B200 + NCCL all-gather merge" if world > 1 else ", single B200")),
                 "corpus_rows": total_rows, "rows_per_gpu": shard_rows, "dim": D, "k": K_TOP, "batch": Q,
-                "arithmetic": "bf16 operands / fp32 accumulate scan, exact fp32 rescore of the final candidates",
+                "arithmetic": ("fp16" if int(flat.get_param("scan_dtype")) == 1 else "bf16")
+                + " operands / fp32 accumulate tcgen05 scan (unit-norm rows), exact fp32 rescore of the final candidates",
                 "l2_policy": "no flush: corpus (bf16 scan copy + fp32 master) is larger than the 126 MB L2",
                 "corpus_build_s": round(t_build, 2),
             },
@@ -405,6 +408,8 @@ def main():
     ap.add_argument("--corpus-rows", type=int, default=0, help="override total corpus rows")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scan-dtype", choices=["auto", "bf16", "fp16"], default="auto",
+                    help="16-bit format of the scan copy (auto = fp16 for L2-normalised corpora)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

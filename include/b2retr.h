@@ -97,11 +97,12 @@ int b2r_index_set_ids(b2r_index* h, int64_t n, const int64_t* ids, void* stream)
 /* Added to every returned label (row-sharded corpora: global = base + local). */
 int b2r_index_set_label_base(b2r_index* h, int64_t base);
 
-/* Tunables (all have defaults): rescore_eps = relative bf16 score error bound
- * used for the rescore window (default 2^-8 * 1.02 = rigorous for bf16 operands,
- * fp32 accumulate); cand_factor = target candidates per query as a multiple of k
- * (default 4); cand_cap = candidate slots per query (default 4096, power of two,
- * <= 4096). */
+/* Tunables (all have defaults): scan_dtype = -1 auto | 0 bf16 | 1 fp16 (before the first
+ * add; auto = fp16 while every add normalised its rows, else bf16 — same tensor rate, fp16 has
+ * an 8x smaller rounding error hence a smaller rescore window); rescore_eps = relative scan
+ * score error bound for the rescore window (default 2^-8*1.02 bf16 / 2^-10*1.02 fp16 =
+ * rigorous); cand_factor = target candidates per query as a multiple of k (default 4 bf16 /
+ * 2.5 fp16); rescore = 0 returns scan scores of the unit-norm query instead of exact fp32. */
 int b2r_index_set_param(b2r_index* h, const char* name, double value);
 double b2r_index_get_param(const b2r_index* h, const char* name);
 
@@ -201,8 +202,10 @@ int b2r_tower_forward(b2r_tower* t, const int64_t* cat, const float* num, int64_
 /* ---------------------------------------------------------------- debug -- */
 /* Test-only helpers (never on the product path). */
 
-/* Full bf16-operand / fp32-accumulate score matrix through the SAME tcgen05
- * scan kernel in dump mode: out fp32 [q, ntotal]. */
+/* Full 16-bit-operand / fp32-accumulate SCAN score matrix through the SAME tcgen05 scan
+ * kernel in dump mode: out fp32 [q, ntotal].  Scan scores are those of the UNIT-NORM
+ * query copy against the stored scan rows (the product path thresholds on these and
+ * re-scores the survivors exactly in fp32 with the caller's query scale). */
 int b2r_debug_scores_tc(b2r_index* h, int q, const float* queries, int normalize, float* out,
                         void* workspace, size_t ws_bytes, void* stream);
 /* The same matrix from a plain CUDA-core loop (no TMA / tensor cores). */

@@ -9,6 +9,7 @@
 //                   [DUMP scan -> kth_value + compaction]    (small corpus, "dense")
 //                -> FILTER scan (score >= tau -> candidate buffers)
 //                -> select_rescore (sort, provable rescore window, exact fp32, id map)
+#include <cuda_fp16.h>
 #include <math.h>
 #include <string.h>
 
@@ -59,7 +60,7 @@ Plan make_plan(const b2r_index* h, int q, int k, bool have_tau) {
   const int64_t N = h->ntotal;
   pl.tiles = (int)ceil_div(N > 0 ? N : 1, kTileRows);
   const int cap = h->cand_cap;  // candidates per query the select kernel holds (4096)
-  int ct = (int)llround(h->cand_factor * k);
+  int ct = (int)llround((h->scan_fp16 == 1 ? h->cand_factor_fp16 : h->cand_factor) * k);
   if (ct < 64) ct = 64;
   const int ct_max = (cap * 5) / 8;  // leave head-room for sampling noise
   if (ct > ct_max) ct = ct_max;
@@ -176,7 +177,9 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
   int MQ, QG, splits;
   plan_scan(q, pl.tiles, h->num_sms, &MQ, &QG, &splits);
   const int qpad = QG * MQ * kQBlock;  // <= pl.qpad
-  if ((rc = launch_prep_queries(queries, q, qpad, d, normalize, q32, q16, qnorm, stream))) return rc;
+  const int fp16 = h->scan_fp16 == 1;
+  const float eps = (float)(fp16 ? h->eps_fp16 : h->eps);
+  if ((rc = launch_prep_queries(queries, q, qpad, d, normalize, q32, q16, fp16, qnorm, stream))) return rc;
   CUtensorMap tmQ;
   if ((rc = make_tmap_bf16_rows(&tmQ, q16, qpad, d))) return rc;
   if ((rc = launch_fill_f32(tau, qpad, INFINITY, stream))) return rc;
@@ -191,6 +194,7 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
   sp.tile_stride = 1;
   sp.tile_count = pl.tiles;
   sp.splits = splits;
+  sp.idesc = scan_idesc(fp16);
   sp.tau = tau;
   // the planned split count fixes the segment geometry; this chunk may use fewer splits
   if (splits > pl.splits) splits = pl.splits;
@@ -211,7 +215,7 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
     // exact k-th bf16 score per query, threshold = k-th - 2E: the candidates ARE the provable window
     const int m = (int64_t)k < h->ntotal ? k : (int)h->ntotal;
     if ((rc = launch_kth_value(aux, q, h->ntotal, pl.dump_ld, m, tau, count, cand, pl.cap_seg,
-                               h->rescore ? qnorm : nullptr, h->maxnorm, (float)h->eps, stream)))
+                               h->rescore ? qnorm : nullptr, h->maxnorm, eps, stream)))
       return rc;
     sel_nseg = 1;
     sel_cap_seg = pl.cap_seg;
@@ -252,7 +256,7 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
   sel.qnorm = qnorm;
   sel.x32 = h->x32;
   sel.maxnorm = h->maxnorm;
-  sel.eps = (float)h->eps;
+  sel.eps = eps;
   sel.rescore = h->rescore;
   sel.ids = (h->ids && h->n_ids >= h->ntotal) ? h->ids : nullptr;
   sel.label_base = h->label_base;
@@ -301,8 +305,15 @@ int flat_add(b2r_index* h, int64_t n, const float* x, int normalize, cudaStream_
   if (h->ntotal + n > 0x7FFFFF00ll) return fail(B2R_EUNSUPPORTED, "index_add: more than 2^31 rows per shard");
   int rc = ensure_capacity(h, h->ntotal + n, stream);
   if (rc) return rc;
+  // scan format: fp16 while every stored row was normalised on ingest (|x_i| <= 1), else bf16
+  int want16 = h->scan_dtype_req >= 0 ? h->scan_dtype_req : (normalize ? 1 : 0);
+  if (h->ntotal > 0 && h->scan_fp16 == 0 && h->scan_dtype_req < 0) want16 = 0;   // once bf16, stay bf16
+  if (h->ntotal > 0 && h->scan_fp16 >= 0 && h->scan_fp16 != want16) {
+    if ((rc = launch_reencode(h->x32, h->ntotal, h->d, h->x16, want16, stream))) return rc;
+  }
+  h->scan_fp16 = want16;
   rc = launch_ingest(x, n, h->d, normalize, h->x32 + (size_t)h->ntotal * h->d,
-                     h->x16 + (size_t)h->ntotal * h->d, h->maxnorm, stream);
+                     h->x16 + (size_t)h->ntotal * h->d, want16, h->maxnorm, stream);
   if (rc) return rc;
   h->ntotal += n;
   return make_tmap_bf16_rows(&h->tmX, h->x16, h->ntotal, h->d);
@@ -471,8 +482,13 @@ int b2r_index_set_label_base(b2r_index* h, int64_t base) {
 int b2r_index_set_param(b2r_index* h, const char* name, double value) {
   if (!h || !name) return fail(B2R_EINVAL, "index_set_param: NULL argument");
   const std::string n(name);
-  if (n == "rescore_eps") { if (value < 0) return fail(B2R_EINVAL, "rescore_eps < 0"); h->eps = value; }
-  else if (n == "cand_factor") { if (value < 1) return fail(B2R_EINVAL, "cand_factor < 1"); h->cand_factor = value; }
+  if (n == "rescore_eps") { if (value < 0) return fail(B2R_EINVAL, "rescore_eps < 0"); h->eps = value; h->eps_fp16 = value; }
+  else if (n == "scan_dtype") {
+    // -1 auto, 0 bf16, 1 fp16 (only for corpora whose rows are normalised on ingest); set before the first add
+    if (h->ntotal > 0) return fail(B2R_ESTATE, "scan_dtype must be set before the first add");
+    h->scan_dtype_req = (int)value;
+  }
+  else if (n == "cand_factor") { if (value < 1) return fail(B2R_EINVAL, "cand_factor < 1"); h->cand_factor = value; h->cand_factor_fp16 = value; }
   else if (n == "cand_cap") {
     const int c = (int)value;
     if (c < 64 || c > 4096 || (c & (c - 1))) return fail(B2R_EINVAL, "cand_cap must be a power of two in [64,4096]");
@@ -500,7 +516,8 @@ int b2r_index_set_param(b2r_index* h, const char* name, double value) {
 double b2r_index_get_param(const b2r_index* h, const char* name) {
   if (!h || !name) return NAN;
   const std::string n(name);
-  if (n == "rescore_eps") return h->eps;
+  if (n == "rescore_eps") return h->scan_fp16 == 1 ? h->eps_fp16 : h->eps;
+  if (n == "scan_dtype") return h->scan_fp16;
   if (n == "cand_factor") return h->cand_factor;
   if (n == "cand_cap") return h->cand_cap;
   if (n == "rescore") return h->rescore;
@@ -577,7 +594,7 @@ int b2r_debug_scores_tc(b2r_index* h, int q, const float* queries, int normalize
   float* q32 = reinterpret_cast<float*>(ws + align_up((size_t)qpad * h->d * 2, 256));
   float* qn = reinterpret_cast<float*>(ws + align_up((size_t)qpad * h->d * 2, 256) + align_up((size_t)qpad * h->d * 4, 256));
   int rc;
-  if ((rc = launch_prep_queries(queries, q, qpad, h->d, normalize, q32, q16, qn, stream))) return rc;
+  if ((rc = launch_prep_queries(queries, q, qpad, h->d, normalize, q32, q16, h->scan_fp16 == 1, qn, stream))) return rc;
   CUtensorMap tmQ;
   if ((rc = make_tmap_bf16_rows(&tmQ, q16, qpad, h->d))) return rc;
   ScanParams sp;
@@ -590,6 +607,7 @@ int b2r_debug_scores_tc(b2r_index* h, int q, const float* queries, int normalize
   sp.tile_stride = 1;
   sp.tile_count = tiles;
   sp.splits = splits;
+  sp.idesc = scan_idesc(h->scan_fp16 == 1);
   sp.dump = out;
   sp.ld = h->ntotal;
   return launch_scan(SCAN_DUMP, MQ, tmQ, h->tmX, sp, h->num_sms, stream);
@@ -597,38 +615,48 @@ int b2r_debug_scores_tc(b2r_index* h, int q, const float* queries, int normalize
 
 }  // extern "C"
 
-// plain CUDA-core reference of the same bf16 x bf16 -> fp32 contraction (test-only)
+// plain CUDA-core reference of the same 16-bit x 16-bit -> fp32 contraction (test-only): the query's
+// scan copy is unit-norm (as in the product path), rounded to the index's scan format
 namespace {
-__global__ void scores_simt_kernel(const __nv_bfloat16* __restrict__ x16, int64_t N, int d,
-                                   const float* __restrict__ qin, int Q, int normalize,
-                                   float* __restrict__ out) {
+__device__ __forceinline__ float scan16_to_float(uint16_t bits, int fp16) {
+  if (fp16) return __half2float(__ushort_as_half(bits));
+  return __uint_as_float((uint32_t)bits << 16);
+}
+__device__ __forceinline__ float round_scan16(float v, int fp16) {
+  if (fp16) return __half2float(__float2half_rn(v));
+  return __bfloat162float(__float2bfloat16_rn(v));
+}
+__global__ void scores_simt_kernel(const uint16_t* __restrict__ x16, int64_t N, int d,
+                                   const float* __restrict__ qin, int Q, int fp16, float* __restrict__ out) {
   const int q = blockIdx.y;
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   __shared__ float qs[1024];
   __shared__ float s_scale;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
     float ss = 0.f;
-    for (int i = 0; i < d; ++i) ss += qin[(size_t)q * d + i] * qin[(size_t)q * d + i];
-    s_scale = (normalize && ss > 0.f) ? 1.0f / sqrtf(ss) : 1.0f;
+    for (int i = threadIdx.x; i < d; i += 32) ss += qin[(size_t)q * d + i] * qin[(size_t)q * d + i];
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (threadIdx.x == 0) s_scale = ss > 0.f ? 1.0f / sqrtf(ss) : 1.0f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < d; i += blockDim.x)
-    qs[i] = __bfloat162float(__float2bfloat16_rn(qin[(size_t)q * d + i] * s_scale));
+  for (int i = threadIdx.x; i < d; i += blockDim.x) qs[i] = round_scan16(qin[(size_t)q * d + i] * s_scale, fp16);
   __syncthreads();
   if (row >= N) return;
   float acc = 0.f;
-  for (int i = 0; i < d; ++i) acc = fmaf(qs[i], __bfloat162float(x16[(size_t)row * d + i]), acc);
+  for (int i = 0; i < d; ++i) acc = fmaf(qs[i], scan16_to_float(x16[(size_t)row * d + i], fp16), acc);
   out[(size_t)q * N + row] = acc;
 }
 }  // namespace
 
 extern "C" int b2r_debug_scores_simt(b2r_index* h, int q, const float* queries, int normalize, float* out,
                                      void* stream_) {
+  (void)normalize;
   if (!h || q <= 0 || !queries || !out) return fail(B2R_EINVAL, "debug_scores_simt: bad arguments");
   if (h->ntotal == 0) return B2R_OK;
   DeviceGuard g(h->device);
   dim3 grid((unsigned)ceil_div(h->ntotal, 256), (unsigned)q);
-  scores_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(h->x16, h->ntotal, h->d, queries, q, normalize, out);
+  scores_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(reinterpret_cast<const uint16_t*>(h->x16), h->ntotal,
+                                                              h->d, queries, q, h->scan_fp16 == 1, out);
   B2R_CHECK_LAUNCH("scores_simt_kernel");
   return B2R_OK;
 }

@@ -38,8 +38,13 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // Width of the rescore window below the k-th bf16 score: 2E, E = eps * |q| * max|x| bounds
 // |bf16 score - exact score|.  One definition so every kernel computes the identical float.
 __host__ __device__ inline float rescore_margin(float eps, float qnorm, float maxnorm) {
-  return 2.0f * (eps * qnorm * maxnorm * 1.0001f);
+  // + 4e-6 * qnorm: absolute slack for fp16 subnormal flushing (|x_i| < 2^-14) and fp32 accumulation
+  return 2.0f * (eps * qnorm * maxnorm * 1.0001f + 4e-6f * qnorm);
 }
+// 16-bit scan formats (same tcgen05 kind::f16 rate): bf16 = range of fp32, 8-bit significand;
+// fp16 = 11-bit significand (8x smaller rounding error) but |x| <= 65504 — used when every stored
+// row was L2-normalised on ingest (|x_i| <= 1); the query's scan copy is always unit-norm.
+enum ScanDtype { SCAN_BF16 = 0, SCAN_FP16 = 1 };
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ------------------------------------------------------------ scan kernel ---
@@ -59,6 +64,7 @@ struct ScanParams {
   int tile_stride;
   int tile_count;
   int splits;       // unit u -> (split = u / QG, qg = u % QG)
+  uint32_t idesc;   // tcgen05 instruction descriptor (operand format bf16 or fp16, M=128, N=128)
   // FILTER: candidates go to private segments, one per (query, corpus split[, column half]):
   // exactly one warp ever writes a segment, so an append is a plain store + register counter.
   const float* tau;      // [Qpad] candidate threshold (score >= tau passes); +inf for padding
@@ -85,10 +91,14 @@ void plan_scan(int Q, int tile_count, int num_sms, int* MQ, int* QG, int* splits
 // rows fp32 [n,d] -> (optional L2 normalise) -> fp32 master + bf16 copy; updates *maxnorm
 // (device float, atomic max of the stored rows' L2 norms).
 int launch_ingest(const float* x, int64_t n, int d, int normalize, float* out32,
-                  __nv_bfloat16* out16, float* maxnorm, cudaStream_t stream);
-// queries fp32 [q,d] -> q32 [qpad,d], q16 [qpad,d] (zero padded), qnorm [qpad]
+                  __nv_bfloat16* out16, int fp16, float* maxnorm, cudaStream_t stream);
+// queries fp32 [q,d] -> q32 [qpad,d] (normalised iff `normalize`), q16 [qpad,d] = ALWAYS unit-norm
+// 16-bit scan copy (zero padded), qnorm [qpad] = norm of the scan copy (1, or 0 for a zero query)
 int launch_prep_queries(const float* x, int q, int qpad, int d, int normalize, float* q32,
-                        __nv_bfloat16* q16, float* qnorm, cudaStream_t stream);
+                        __nv_bfloat16* q16, int fp16, float* qnorm, cudaStream_t stream);
+// re-encode the 16-bit scan copy of n rows from the fp32 master
+int launch_reencode(const float* x32, int64_t n, int d, __nv_bfloat16* out16, int fp16, cudaStream_t stream);
+uint32_t scan_idesc(int fp16);
 
 // ------------------------------------------------------------------ select ---
 // per-row m-th largest of vals[r, 0..T) (ld stride) -> tau[r]; if cand_* given, also
@@ -140,7 +150,11 @@ struct b2r_index {
   CUtensorMap tmX;
   bool trained = true;
   // tunables
-  double eps = 0.00390625 * 1.02;  // 2^-8 (two bf16 roundings per product), 2% slack
+  double eps = 0.00390625 * 1.02;  // bf16: 2^-8 (two roundings of 2^-9 per product), 2% slack
+  double eps_fp16 = 0.0009765625 * 1.02;  // fp16: 2^-10
+  int scan_dtype_req = -1;  // -1 auto (fp16 while every add was normalised), 0 bf16, 1 fp16
+  int scan_fp16 = -1;       // current format of x16 (-1: nothing stored yet)
+  double cand_factor_fp16 = 2.5;
   double cand_factor = 4.0;
   int cand_cap = 4096;
   int rescore = 1;

@@ -267,6 +267,7 @@ struct IvfScanParams {
   const int* num_units;
   int max_units;
   int d;
+  uint32_t idesc;
   const int* pair_sorted;     // gathered row -> pair id
   const int64_t* pair_out;    // pair id -> offset of its score run in scorebuf
   float* scorebuf;
@@ -328,7 +329,7 @@ ivf_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 128);
+      const uint32_t idesc = p.idesc;
       int slot = 0, tb = 0;
       uint32_t ph = 0, tph = 0, qf_par = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -706,8 +707,15 @@ int ivf_add(b2r_index* h, int64_t n, const float* x, int normalize, cudaStream_t
   DevBuf t32, t16, assign, hist, new_off, cursor, dst_old, dst_new;
   if ((rc = t32.alloc((size_t)n * d * 4))) return rc;
   if (!is_pq && (rc = t16.alloc((size_t)n * d * 2))) return rc;
-  if ((rc = launch_ingest(x, n, d, normalize, t32.as<float>(), is_pq ? nullptr : t16.as<__nv_bfloat16>(), h->maxnorm,
-                          stream)))
+  // scan format: fp16 while every stored row was normalised on ingest (|x_i| <= 1), else bf16
+  int want16 = h->scan_dtype_req >= 0 ? h->scan_dtype_req : (normalize ? 1 : 0);
+  if (h->ntotal > 0 && h->scan_fp16 == 0 && h->scan_dtype_req < 0) want16 = 0;   // once bf16, stay bf16
+  if (!is_pq && h->ntotal > 0 && h->scan_fp16 >= 0 && h->scan_fp16 != want16) {
+    if ((rc = launch_reencode(h->x32, h->ntotal, d, h->x16, want16, stream))) return rc;
+  }
+  h->scan_fp16 = want16;
+  if ((rc = launch_ingest(x, n, d, normalize, t32.as<float>(), is_pq ? nullptr : t16.as<__nv_bfloat16>(), want16,
+                          h->maxnorm, stream)))
     return rc;
   // 2. list assignment: exact max-inner-product centroid (faiss quantizer->assign)
   if ((rc = assign.alloc((size_t)n * 8))) return rc;
@@ -902,7 +910,9 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     uint2* cand = reinterpret_cast<uint2*>(ws + pl.off_cand);
     float* scorebuf = reinterpret_cast<float*>(ws + pl.off_score);
     int rc;
-    if ((rc = launch_prep_queries(queries + (size_t)q0 * d, qc, qpad, d, normalize, q32, q16, qnorm, stream))) return rc;
+    if ((rc = launch_prep_queries(queries + (size_t)q0 * d, qc, qpad, d, normalize, q32, q16, h->scan_fp16 == 1, qnorm,
+                                  stream)))
+      return rc;
     // coarse quantiser: exact top-nprobe centroids, best first (faiss quantizer->search)
     if ((rc = flat_search(h->quantizer, qc, q32, 0, np, cdist, coarse, nullptr, nullptr, nullptr, ws + pl.off_qws,
                           pl.qws_bytes, stream)))
@@ -937,6 +947,7 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     sp.num_units = nunits;
     sp.max_units = pl.max_units;
     sp.d = d;
+    sp.idesc = scan_idesc(h->scan_fp16 == 1);
     sp.pair_sorted = pair_sorted;
     sp.pair_out = pair_out;
     sp.scorebuf = scorebuf;
@@ -945,7 +956,7 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     }
     ivf_threshold_kernel<<<qc, kIvfSelThreads, (size_t)np * 16, stream>>>(
         scorebuf, pl.smax, row_len, k, coarse, np, h->list_off, tau, count, cand, pl.cap,
-        (h->rescore && !is_pq) ? qnorm : nullptr, h->maxnorm, (float)h->eps);
+        (h->rescore && !is_pq) ? qnorm : nullptr, h->maxnorm, (float)(h->scan_fp16 == 1 ? h->eps_fp16 : h->eps));
     B2R_CHECK_LAUNCH("ivf_threshold_kernel");
     SelectParams sel;
     memset(&sel, 0, sizeof(sel));
@@ -962,7 +973,7 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     sel.qnorm = qnorm;
     sel.x32 = h->x32;
     sel.maxnorm = h->maxnorm;
-    sel.eps = (float)h->eps;
+    sel.eps = (float)(h->scan_fp16 == 1 ? h->eps_fp16 : h->eps);
     sel.rescore = is_pq ? 0 : h->rescore;   // ADC distances are the result (faiss does not re-rank)
     sel.negate_out = is_pq ? 1 : 0;
     sel.perm = h->perm;

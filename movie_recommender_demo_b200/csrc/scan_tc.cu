@@ -187,7 +187,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   } else if (warp == 1) {
     if (lane == 0) {
       // ================================================ MMA issuer
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 128);
+      const uint32_t idesc = p.idesc;
       int slot = 0, tb = 0;
       uint32_t ph = 0, tph = 0, qf_par = 0;
       int last_qg = -1;

@@ -38,6 +38,7 @@ METRIC_INNER_PRODUCT = _lib.METRIC_IP
 METRIC_L2 = _lib.METRIC_L2
 _RETRY_BITS = _lib.ST_TOO_FEW | _lib.ST_NEED_LOWER_TAU | _lib.ST_CAND_OVERFLOW
 _MAX_RETRIES = 8
+_PIPE_CHUNK = 1024   # queries per chunk when device->host result copies are pipelined
 
 
 def _stream_ptr(torch, device) -> int:
@@ -69,6 +70,7 @@ class _DeviceIndex:
         self._ids_set = False
         self.last_status = None  # per-query status bits of the most recent search (numpy)
         self.last_retries = 0
+        self._copy_stream = None
 
     # ------------------------------------------------------------ lifetime
     def __del__(self):
@@ -186,7 +188,10 @@ class _DeviceIndex:
         overflow) are re-run with the threshold the device suggests; that needs the status on
         the host, which rides along with the result copy."""
         torch = self._torch
+        self.last_retries = 0
         qt = self._to_device_f32(x, "search")
+        if not return_device and qt.shape[0] >= 2 * _PIPE_CHUNK:
+            return self._search_pipelined(qt, k, normalize, nprobe)
         D, I, status, tau_retry = self.search_device(qt, k, normalize=normalize, nprobe=nprobe)
         # results + status ride to pinned host buffers in one batch of async copies, one sync
         st_h = self._to_pinned(status)
@@ -195,9 +200,59 @@ class _DeviceIndex:
             D_h, I_h = self._to_pinned(D), self._to_pinned(I)
         torch.cuda.current_stream(self.device).synchronize()
         st = st_h.numpy()
+        if (st & _RETRY_BITS).any() and self._supports_retry:
+            st = self._retry(qt, k, normalize, nprobe, st.copy(), tau_retry, D, I, None, None)
+            D_h = None  # stale
+        self.last_status = st
+        self._warn_status(st)
+        if return_device:
+            return D, I
+        if D_h is None:
+            D_h, I_h = self._to_pinned(D), self._to_pinned(I)
+            torch.cuda.current_stream(self.device).synchronize()
+        return D_h.numpy(), I_h.numpy()
+
+    def _search_pipelined(self, qt, k, normalize, nprobe):
+        """Large batches: search in chunks of _PIPE_CHUNK queries and copy each chunk's results to
+        pinned host memory on a side stream while the next chunk is being searched."""
+        torch = self._torch
+        nq = qt.shape[0]
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        side = self._copy_stream
+        D_h = torch.empty((nq, k), dtype=torch.float32, pin_memory=True)
+        I_h = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
+        st_h = torch.empty(nq, dtype=torch.int32, pin_memory=True)
+        keep, taus = [], []
+        for lo in range(0, nq, _PIPE_CHUNK):
+            hi = min(nq, lo + _PIPE_CHUNK)
+            D, I, st, tr = self.search_device(qt[lo:hi], k, normalize=normalize, nprobe=nprobe)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                D_h[lo:hi].copy_(D, non_blocking=True)
+                I_h[lo:hi].copy_(I, non_blocking=True)
+                st_h[lo:hi].copy_(st, non_blocking=True)
+            keep.append((D, I, st))     # alive until the side stream is drained
+            taus.append(tr)
+        side.synchronize()
+        st = st_h.numpy()
+        D_np, I_np = D_h.numpy(), I_h.numpy()
+        if (st & _RETRY_BITS).any() and self._supports_retry:
+            st = self._retry(qt, k, normalize, nprobe, st.copy(), torch.cat(taus), None, None, D_np, I_np)
+        self.last_status = st
+        self._warn_status(st)
+        return D_np, I_np
+
+    def _retry(self, qt, k, normalize, nprobe, st, tau_retry, D_dev, I_dev, D_np, I_np):
+        """Re-run the queries the kernels flagged as not provably exact, with the thresholds the
+        device suggested, until none is flagged or no progress is made."""
+        torch = self._torch
         retries = 0
         prev_tau = None
-        while retries < _MAX_RETRIES and self._supports_retry:
+        while retries < _MAX_RETRIES:
             bad = np.nonzero(st & _RETRY_BITS)[0]
             if bad.size == 0:
                 break
@@ -209,24 +264,22 @@ class _DeviceIndex:
             prev_tau = tau_host
             D2, I2, st2, tr2 = self.search_device(qt.index_select(0, bad_t), k, normalize=normalize,
                                                   nprobe=nprobe, tau=tau)
-            D.index_copy_(0, bad_t, D2)
-            I.index_copy_(0, bad_t, I2)
+            if D_dev is not None:
+                D_dev.index_copy_(0, bad_t, D2)
+                I_dev.index_copy_(0, bad_t, I2)
+            else:
+                D_np[bad] = D2.cpu().numpy()
+                I_np[bad] = I2.cpu().numpy()
             tau_retry.index_copy_(0, bad_t, tr2)
-            st = st.copy()
             st[bad] = st2.cpu().numpy()
             retries += 1
-            D_h = None  # stale
-        self.last_status = st
         self.last_retries = retries
+        return st
+
+    def _warn_status(self, st) -> None:
         if (st != 0).any():
             warnings.warn(f"b200 search: {int((st != 0).sum())} queries not provably exact "
                           f"(status bits {sorted(set(int(s) for s in st if s))})")
-        if return_device:
-            return D, I
-        if D_h is None:
-            D_h, I_h = self._to_pinned(D), self._to_pinned(I)
-            torch.cuda.current_stream(self.device).synchronize()
-        return D_h.numpy(), I_h.numpy()
 
     def _to_pinned(self, t):
         """async device->pinned-host copy (torch's caching host allocator recycles the blocks;

@@ -43,21 +43,79 @@ def _parity(fr, N, Q, k, d=256, seed=0, force_path=0, unit=False):
     return res
 
 
+def _round16(a, fp16):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return t.to(torch.float16 if fp16 else torch.bfloat16).to(torch.float32).numpy()
+
+
+@pytest.mark.parametrize("normalize", [False, True])      # un-normalised add -> bf16 scan copy, normalised -> fp16
 @pytest.mark.parametrize("N,Q,d", [(256, 16, 256), (1000, 1, 256), (5000, 130, 256), (70001, 300, 128),
                                    (33, 5, 192), (100000, 64, 64)])
-def test_tcgen05_score_tile_matches_bf16_reference(fr, N, Q, d):
-    """Dump mode of the scan kernel == bf16-operand / fp32-accumulate contraction."""
+def test_tcgen05_score_tile_matches_16bit_reference(fr, N, Q, d, normalize):
+    """Dump mode of the scan kernel == (unit-norm query, 16-bit) x (stored 16-bit rows), fp32 accumulate."""
+    from oracle.flat import normalize_L2
     rng = np.random.default_rng(N + Q)
     x = rng.standard_normal((N, d)).astype(np.float32)
     q = rng.standard_normal((Q, d)).astype(np.float32)
     idx = fr.IndexFlatIP(d)
-    idx.add(x)
+    idx.add(x, normalize=normalize)
+    fp16 = int(idx.get_param("scan_dtype")) == 1
+    assert fp16 == normalize
     tc = idx.debug_scores(q, "tc").cpu().numpy()
     simt = idx.debug_scores(q, "simt").cpu().numpy()
-    ref = _bf16(q).astype(np.float64) @ _bf16(x).astype(np.float64).T
+    xs = idx.reconstruct_n(0, N).cpu().numpy()          # the stored fp32 rows (the 16-bit copy rounds exactly these)
+    ref = _round16(normalize_L2(q.copy()), fp16).astype(np.float64) @ _round16(xs, fp16).astype(np.float64).T
     scale = np.abs(ref).max()
-    assert np.abs(tc - ref).max() <= 2e-6 * scale * np.sqrt(d)
-    assert np.abs(simt - ref).max() <= 2e-6 * scale * np.sqrt(d)
+    # fp32 accumulation-order noise + the odd 16-bit rounding flip of a query element: the GPU normalises
+    # the query with its own summation order, and a 1-ulp fp32 difference can flip one 16-bit rounding
+    # (<= 2^-11 |q_i||x_i| per score for fp16).  A layout / descriptor bug would be O(scale).
+    tol = 2e-6 * scale * np.sqrt(d) + 1e-3 * scale
+    assert np.abs(tc - ref).max() <= tol
+    assert np.abs(simt - ref).max() <= tol
+    assert np.median(np.abs(tc - ref)) <= 1e-6 * scale
+
+
+@pytest.mark.parametrize("scan_dtype", [0, 1])
+def test_both_scan_formats_give_the_exact_answer(fr, scan_dtype):
+    """bf16 (north_star wording) and fp16 scan copies must both reproduce the fp32 oracle; fp16 needs a
+    smaller rescore window."""
+    from oracle.compare import compare_topk
+    from oracle.flat import OracleFAISSIndex
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((300000, 256)).astype(np.float32)
+    q = rng.standard_normal((16, 256)).astype(np.float32)
+    g = fr.FAISSIndex(256, 'Flat')
+    g.index.set_param("scan_dtype", scan_dtype)
+    g.index.set_param("force_path", 2)
+    g.add(x)
+    assert int(g.index.get_param("scan_dtype")) == scan_dtype
+    ids, dist = g.search(q, k=500)
+    o = OracleFAISSIndex(256, 'Flat')
+    o.add(x)
+    rid, rd = o.search(q, k=500, extra=32)
+    compare_topk(ids, dist, rid, rd, 500, gap_tol=GAP_TOL)
+    assert (g.index.last_status == 0).all()
+
+
+def test_unnormalised_faiss_level_index_switches_to_bf16_and_stays_exact(fr):
+    """index.add(x) without normalisation (plain faiss IndexFlatIP semantics) after a normalised add
+    re-encodes the scan copy as bf16; large-magnitude rows and un-normalised queries stay exact."""
+    rng = np.random.default_rng(22)
+    a = rng.standard_normal((3000, 64)).astype(np.float32)
+    b = (rng.standard_normal((2000, 64)) * 300.0).astype(np.float32)      # would overflow an fp16 scan copy
+    idx = fr.IndexFlatIP(64)
+    idx.add(a, normalize=True)
+    assert int(idx.get_param("scan_dtype")) == 1
+    idx.add(b, normalize=False)
+    assert int(idx.get_param("scan_dtype")) == 0
+    q = (rng.standard_normal((5, 64)) * 7.0).astype(np.float32)
+    D, I = idx.search(q, 40, normalize=False)
+    xs = np.concatenate([a / np.linalg.norm(a, axis=1, keepdims=True), b])
+    S = q @ xs.T
+    ref = np.argsort(-S, axis=1, kind="stable")[:, :40]
+    assert np.array_equal(I, ref)
+    np.testing.assert_allclose(D, np.take_along_axis(S, ref, axis=1), rtol=2e-6)
 
 
 @pytest.mark.parametrize("N,Q,k", [(20000, 37, 50), (3000, 5, 500), (100, 3, 500), (1, 2, 10), (4096, 8, 100)])
