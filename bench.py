@@ -313,7 +313,7 @@ def run_b200(args):
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_kind": f"{peaks['source']} STREAM-style copy"}
     roof.update({"kernel": "scan_tc_kernel<MQ,FILTER> (tcgen05 score contraction + threshold filter)",
-                 "kernel_ms": scan_ms, "traffic": _traffic_note(Q)})
+                 "kernel_ms": scan_ms, "traffic": _traffic_note(Q) if shard_rows == CORPUS_1GPU else None})
 
     # ---- timed: e2e through the public API with host buffers
     barrier()

@@ -214,7 +214,7 @@ kth_value_small_kernel(const float* __restrict__ vals, int T, int64_t ld, int m,
 //   5. bitonic sort of the window by (-score, row), gather ids, write top-k
 constexpr int kSel2Threads = 1024;
 
-__global__ void __launch_bounds__(kSel2Threads)
+__global__ void __launch_bounds__(kSel2Threads, 2)
 select_rescore_kernel(const SelectParams p) {
   extern __shared__ __align__(16) uint8_t sm[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(sm);                       // [kKeyCap]
