@@ -111,6 +111,7 @@ int launch_kth_value(const float* vals, int rows, int64_t T, int64_t ld, int m, 
 struct SelectParams {
   int Q, k, d;
   int nseg, cap_seg;     // candidate segments per query / slots per segment
+  int key_cap, rescore_max;  // set by the launcher: shared-memory key / window capacities
   int64_t N;
   const int* cand_count; // [Q, nseg]
   const uint2* cand;     // [Q, nseg, cap_seg]

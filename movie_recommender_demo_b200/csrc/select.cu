@@ -22,8 +22,10 @@ namespace b2r {
 namespace {
 
 constexpr int kSelThreads = 512;
-constexpr int kRescoreMax = 2048;  // rescore window slots
-constexpr int kKeyCap = 4096;      // candidates per query the select kernel can hold
+constexpr int kRescoreMaxBig = 2048;  // rescore window slots (k > 96)
+constexpr int kKeyCapBig = 4096;      // candidates per query the select kernel can hold (k > 96)
+constexpr int kRescoreMaxSmall = 256; // small-k variant (coarse quantiser, k-means assignment): 256 threads,
+constexpr int kKeyCapSmall = 1024;    // ~12 KB of shared memory -> many CTAs per SM
 
 __device__ __forceinline__ uint64_t make_key(float score, uint32_t idx) {
   return ((uint64_t)f2ord(score) << 32) | (uint64_t)(0xFFFFFFFFu - idx);
@@ -217,8 +219,9 @@ constexpr int kSel2Threads = 1024;
 __global__ void __launch_bounds__(kSel2Threads, 2)
 select_rescore_kernel(const SelectParams p) {
   extern __shared__ __align__(16) uint8_t sm[];
-  uint64_t* keys = reinterpret_cast<uint64_t*>(sm);                       // [kKeyCap]
-  uint64_t* rkeys = keys + kKeyCap;                                        // [kRescoreMax]
+  const int kKeyCap = p.key_cap, kRescoreMax = p.rescore_max;             // per-launch capacities
+  uint64_t* keys = reinterpret_cast<uint64_t*>(sm);                       // [key_cap]
+  uint64_t* rkeys = keys + kKeyCap;                                        // [rescore_max]
   float* qv = reinterpret_cast<float*>(rkeys + kRescoreMax);               // [d]
   __shared__ int hist[256];
   __shared__ uint32_t s_prefix;
@@ -235,7 +238,7 @@ select_rescore_kernel(const SelectParams p) {
     // one coalesced load, offsets come from a block-wide exclusive scan (shared memory), then
     // every (segment, lane) pair copies its entries, so all the segment reads are in flight at
     // once instead of one latency per segment.
-    int* soff = reinterpret_cast<int*>(rkeys);   // [nseg + 1] scratch (rkeys is free until later)
+    int* soff = reinterpret_cast<int*>(qv + p.d);  // [nseg + 1] scratch behind the query vector
     for (int sgi = tid; sgi < p.nseg; sgi += blockDim.x) {
       const int produced = p.cand_count[(size_t)q * p.nseg + sgi];
       if (produced > p.cap_seg) s_over = 1;
@@ -464,21 +467,26 @@ int launch_kth_value(const float* vals, int rows, int64_t T, int64_t ld, int m, 
   return B2R_OK;
 }
 
-int launch_select_rescore(const SelectParams& p, cudaStream_t stream) {
+int launch_select_rescore(const SelectParams& p_in, cudaStream_t stream) {
+  SelectParams p = p_in;
   if (p.Q <= 0) return B2R_OK;
+  const bool small = p.k <= 96;
+  p.key_cap = small ? kKeyCapSmall : kKeyCapBig;
+  p.rescore_max = small ? kRescoreMaxSmall : kRescoreMaxBig;
+  const int threads = small ? 256 : kSel2Threads;
   if (p.nseg < 1 || p.cap_seg < 1) return fail(B2R_EINVAL, "select: bad candidate segment layout");
-  if (p.k > kRescoreMax / 2) return fail(B2R_EUNSUPPORTED, "select: k must be <= 1024");
+  if (p.k > kRescoreMaxBig / 2) return fail(B2R_EUNSUPPORTED, "select: k must be <= 1024");
   if (p.d % 4 != 0) return fail(B2R_EINVAL, "select: d must be a multiple of 4");
-  const size_t smem = (size_t)kKeyCap * 8 + (size_t)kRescoreMax * 8 + (size_t)p.d * 4;
+  const size_t smem = (size_t)p.key_cap * 8 + (size_t)p.rescore_max * 8 + (size_t)p.d * 4 + (size_t)(p.nseg + 1) * 4;
   static bool configured[64] = {};
   int dev = 0;
   B2R_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
     B2R_CUDA(cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  4096 * 8 + kRescoreMax * 8 + 1024 * 4));
+                                  kKeyCapBig * 8 + kRescoreMaxBig * 8 + 1024 * 4 + 8192 * 4));
     configured[dev & 63] = true;
   }
-  select_rescore_kernel<<<p.Q, kSel2Threads, smem, stream>>>(p);
+  select_rescore_kernel<<<p.Q, threads, smem, stream>>>(p);
   B2R_CHECK_LAUNCH("select_rescore_kernel");
   return B2R_OK;
 }

@@ -1,0 +1,32 @@
+"""Profiling driver for the IVF paths: python tests/prof_ivf.py KIND Q [N] [nlist] [steps]"""
+import sys
+import time
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import torch
+from movie_recommender_demo_b200.faiss_retrieval import FAISSIndex
+FAISSIndex.verbose = False
+kind = sys.argv[1] if len(sys.argv) > 1 else "IVF"
+Q = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+N = int(sys.argv[3]) if len(sys.argv) > 3 else 2_000_000
+nlist = int(sys.argv[4]) if len(sys.argv) > 4 else 1024
+steps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+dev = torch.device("cuda", 0)
+g = torch.Generator(device=dev).manual_seed(3)
+centres = torch.randn((nlist, 256), generator=g, device=dev)
+x = torch.empty((N, 256), device=dev)
+for lo in range(0, N, 1 << 20):
+    hi = min(N, lo + (1 << 20))
+    x[lo:hi] = centres[torch.randint(0, nlist, (hi - lo,), generator=g, device=dev)] + 0.35 * torch.randn((hi - lo, 256), generator=g, device=dev)
+x = torch.nn.functional.normalize(x, dim=1)
+idx = FAISSIndex(256, kind, nlist=nlist, nprobe=32, pq_m=32)
+idx.add(x)
+q = torch.nn.functional.normalize(centres[torch.randint(0, nlist, (Q,), generator=g, device=dev)] + 0.35 * torch.randn((Q, 256), generator=g, device=dev), dim=1)
+for _ in range(2):
+    idx.index.search_device(q, 500, normalize=True)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(steps):
+    idx.index.search_device(q, 500, normalize=True)
+torch.cuda.synchronize()
+print(f"{kind} N={N} nlist={nlist} Q={Q}: {(time.perf_counter() - t0) / steps * 1e3:.3f} ms/step")

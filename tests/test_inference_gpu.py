@@ -142,3 +142,38 @@ def test_save_load_round_trip(system):
     b, db = loaded.search(q, k=50)
     assert np.array_equal(a, b) and np.array_equal(da, db)
     assert a[:, 0].tolist() == list(range(7))
+
+
+def test_build_faiss_index_device_pipeline(system, tmp_path):
+    """training_pipeline.build_faiss_index shape: AdTower over a Dataset -> IVF(100, 10) index -> save;
+    the saved index answers like an oracle IVF index on the same embeddings and centroids."""
+    import torch
+    from movie_recommender_demo_b200.training_pipeline import build_faiss_index
+    from oracle.compare import compare_topk
+    from oracle.flat import OracleFAISSIndex
+    from weights import make_inputs
+
+    class _Ads(torch.utils.data.Dataset):          # item layout of the reference's AdDataset
+        def __init__(self, cat):
+            self.cat = torch.from_numpy(cat)
+
+        def __len__(self):
+            return len(self.cat)
+
+        def __getitem__(self, i):
+            return {'ad_categorical': self.cat[i]}
+
+    _, _, acat = make_inputs(system["cfg"], 41, 12000)
+    path = str(tmp_path / "faiss_index.bin")
+    index = build_faiss_index(system["model"], _Ads(acat), "cuda", path, batch_size=2048)
+    assert index.index_type == 'IVF' and index.nlist == 100 and index.nprobe == 10
+    assert index.index.ntotal == 12000 and index.id_map == list(range(12000))
+    with torch.no_grad():
+        emb = system["model"].get_ad_embeddings(torch.from_numpy(acat).cuda()).cpu().numpy()
+    o = OracleFAISSIndex(256, 'IVF', nlist=100, nprobe=10)
+    o.index.set_centroids(index.index.export_centroids())
+    o.add(emb)
+    assert np.array_equal(index.index.list_sizes(), o.index.list_sizes())
+    ids, d = index.search(emb[:8], k=100)
+    rid, rd = o.search(emb[:8], k=100, extra=32)
+    compare_topk(ids, d, rid, rd, 100, gap_tol=1e-6)
