@@ -328,8 +328,11 @@ ivf_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer: uniform loop for the whole warp, one elected lane issues (see scan_tc.cu)
+    {
       const uint32_t idesc = p.idesc;
+      const uint64_t adesc0 = umma_desc_kmajor_sw128(sA);
+      const uint64_t bdesc0 = umma_desc_kmajor_sw128(sB);
       int slot = 0, tb = 0;
       uint32_t ph = 0, tph = 0, qf_par = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -343,18 +346,26 @@ ivf_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int kc = 0; kc < KC; ++kc) {
             mbar_wait(bar_full(slot), ph, 25);
             tc_fence_after_sync();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(tb * 128);
+            if (elect_one()) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)(tb * 128);
+              const uint64_t ad = adesc0 + (uint64_t)((kc * 16384) >> 4);
+              const uint64_t bd = bdesc0 + (uint64_t)((slot * 16384) >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_ss(d_tmem, umma_desc_kmajor_sw128(sA + kc * 16384 + k * 32),
-                           umma_desc_kmajor_sw128(sB + slot * 16384 + k * 32), idesc, (uint32_t)((kc | k) != 0));
-            umma_commit(bar_empty(slot));
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ss(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (uint32_t)((kc | k) != 0));
+              umma_commit(bar_empty(slot));
+            }
+            __syncwarp();
             if (++slot == NS) { slot = 0; ph ^= 1; }
           }
-          umma_commit(bar_tfull(tb));
+          if (elect_one()) umma_commit(bar_tfull(tb));
+          __syncwarp();
           if (++tb == NB) { tb = 0; tph ^= 1; }
         }
-        if (u + (int)gridDim.x < units) umma_commit(bar_qempty);
+        if (u + (int)gridDim.x < units) {
+          if (elect_one()) umma_commit(bar_qempty);
+          __syncwarp();
+        }
       }
     }
   } else if (warp >= 4) {

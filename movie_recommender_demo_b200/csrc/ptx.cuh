@@ -98,6 +98,18 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   return p;
 }
 
+// one elected lane of a fully converged warp (the compiler then knows the guarded region is
+// single-threaded and can keep tcgen05 operands in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------- tcgen05
 // TMEM allocation: one full warp executes; base address lands in smem.
 template <int kCols>

@@ -185,9 +185,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================================================ MMA issuer
+    // ================================================== MMA issuer
+    // The whole warp walks the loop (uniform control flow, every lane polls the barriers); one
+    // elected lane issues the tcgen05.mma / commit.  Descriptors are base + 16-byte-unit offsets.
+    {
       const uint32_t idesc = p.idesc;
+      const uint64_t adesc0 = umma_desc_kmajor_sw128(sA);
+      const uint64_t bdesc0 = umma_desc_kmajor_sw128(sB);
       int slot = 0, tb = 0;
       uint32_t ph = 0, tph = 0, qf_par = 0;
       int last_qg = -1;
@@ -207,24 +211,31 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           for (int kc = 0; kc < KC; ++kc) {
             mbar_wait(bar_full(slot), ph, 5);
             tc_fence_after_sync();
+            if (elect_one()) {
 #pragma unroll
-            for (int h = 0; h < MQ; ++h) {
-              const uint32_t d_tmem = tmem_base + (uint32_t)((tb * MQ + h) * 128);
+              for (int h = 0; h < MQ; ++h) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)((tb * MQ + h) * 128);
+                const uint64_t ad = adesc0 + (uint64_t)(((h * 4 + kc) * 16384) >> 4);
+                const uint64_t bd = bdesc0 + (uint64_t)((slot * 16384) >> 4);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {  // 4 x K=16 per 64-element chunk, +32 B inside the swizzle span
-                const uint64_t adesc = umma_desc_kmajor_sw128(sA + (h * 4 + kc) * 16384 + k * 32);
-                const uint64_t bdesc = umma_desc_kmajor_sw128(sB + slot * 16384 + k * 32);
-                umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (uint32_t)((kc | k) != 0));
+                for (int k = 0; k < 4; ++k)  // 4 x K=16 per 64-element chunk: +32 B inside the swizzle span
+                  umma_bf16_ss(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc,
+                               (uint32_t)((kc | k) != 0));
               }
+              umma_commit(bar_empty(slot));  // frees the smem slot when these MMAs retire
             }
-            umma_commit(bar_empty(slot));  // frees the smem slot when these MMAs retire
+            __syncwarp();
             if (++slot == NS) { slot = 0; ph ^= 1; }
           }
-          umma_commit(bar_tfull(tb));  // accumulator complete -> epilogue
+          if (elect_one()) umma_commit(bar_tfull(tb));  // accumulator complete -> epilogue
+          __syncwarp();
           if (++tb == NB) { tb = 0; tph ^= 1; }
         }
         const int nu = u + gridDim.x;
-        if (nu < units && (nu % p.QG) != qg) umma_commit(bar_qempty);
+        if (nu < units && (nu % p.QG) != qg) {
+          if (elect_one()) umma_commit(bar_qempty);
+          __syncwarp();
+        }
       }
     }
   } else if (warp >= kEpiWarp0) {

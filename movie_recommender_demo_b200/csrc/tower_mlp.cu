@@ -184,8 +184,10 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer: uniform loop for the whole warp, one elected lane issues (see scan_tc.cu)
+    {
       constexpr uint32_t idesc = umma_idesc_f16_f32(128, BN);
+      const uint64_t desc0 = umma_desc_kmajor_sw128(base);
       int slot = 0, tb = 0;
       uint32_t ph = 0, tph = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -195,17 +197,19 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int kc = 0; kc < KC; ++kc) {
           mbar_wait(bar_full(slot), ph, 13);
           tc_fence_after_sync();
-          const uint32_t sa = base + slot * Cfg::SLOT;
+          if (elect_one()) {
+            const uint64_t ad = desc0 + (uint64_t)((slot * Cfg::SLOT) >> 4);
+            const uint64_t bd = ad + (uint64_t)(Cfg::SLOT_A >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_bf16_ss(d_tmem, umma_desc_kmajor_sw128(sa + k * 32),
-                         umma_desc_kmajor_sw128(sa + Cfg::SLOT_A + k * 32), idesc,
-                         (uint32_t)((kc | k) != 0));
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (uint32_t)((kc | k) != 0));
+            umma_commit(bar_empty(slot));
           }
-          umma_commit(bar_empty(slot));
+          __syncwarp();
           if (++slot == NS) { slot = 0; ph ^= 1; }
         }
-        umma_commit(bar_tfull(tb));
+        if (elect_one()) umma_commit(bar_tfull(tb));
+        __syncwarp();
         if (++tb == 2) { tb = 0; tph ^= 1; }
       }
     }
