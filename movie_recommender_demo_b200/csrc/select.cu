@@ -470,6 +470,9 @@ int launch_kth_value(const float* vals, int rows, int64_t T, int64_t ld, int m, 
 int launch_select_rescore(const SelectParams& p_in, cudaStream_t stream) {
   SelectParams p = p_in;
   if (p.Q <= 0) return B2R_OK;
+  // k <= 96 (coarse quantiser, k-means assignment): 256 threads, ~12 KB smem -> many queries per SM.
+  // Larger k: one 1024-thread CTA per query, two resident per SM (register cap 32); 256-thread CTAs
+  // were measured slower here (fewer rows in flight during the HBM-bound rescore gather).
   const bool small = p.k <= 96;
   p.key_cap = small ? kKeyCapSmall : kKeyCapBig;
   p.rescore_max = small ? kRescoreMaxSmall : kRescoreMaxBig;

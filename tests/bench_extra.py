@@ -79,7 +79,7 @@ def ivf(kind="IVF"):
     N, d, k = (1_000_000 if SMALL else 10_000_000), 256, 500
     nlist, nprobe = (1024 if SMALL else 4096), 32
     x = _mog(N, d, nlist, seed=3)
-    qs = _mog(4096, d, nlist, seed=4)
+    qs = _mog(4096, d, nlist, seed=3)[torch.randperm(4096, device=dev)]   # queries near the data (same mixture)
     t0 = time.time()
     idx = FAISSIndex(d, kind, nlist=nlist, nprobe=nprobe, pq_m=32)
     idx.train(x)
