@@ -188,7 +188,7 @@ __global__ void pair_runs_kernel(const int64_t* __restrict__ coarse, int Q, int 
     const int64_t l = coarse[(size_t)q * nprobe + j];
     pair_out[(size_t)q * nprobe + j] = (int64_t)q * smax + cum;
     if (l >= 0) {
-      cum += list_off[l + 1] - list_off[l];
+      cum += (list_off[l + 1] - list_off[l] + 3) & ~(int64_t)3;   // runs start 16-byte aligned (float4 stores)
       atomicAdd(list_cnt + l, 1);
     }
   }
@@ -395,12 +395,21 @@ ivf_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               if (lane == 0) mbar_arrive(bar_tempty(tb));
             }
             const int row0 = un.xrow0 + t * kTileRows + col_begin + c * 32;
-            const int nvalid = un.xend - row0;
-            if (outp) {
-              float* dst = outp + (row0 - un.xlist0);
+            const int nvalid = un.xend - row0;                                   // real rows in this chunk
+            const int npad = ((un.xend - un.xlist0 + 3) & ~3) - (row0 - un.xlist0);  // incl. the run's -inf padding
+            if (outp && npad > 0) {
+              float4* dst = reinterpret_cast<float4*>(outp + (row0 - un.xlist0));    // 16-byte aligned by construction
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < nvalid) dst[i] = __uint_as_float(r[i]);
+              for (int i = 0; i < 32; i += 4) {
+                if (i < npad) {
+                  float4 v;
+                  v.x = (i < nvalid) ? __uint_as_float(r[i]) : -INFINITY;
+                  v.y = (i + 1 < nvalid) ? __uint_as_float(r[i + 1]) : -INFINITY;
+                  v.z = (i + 2 < nvalid) ? __uint_as_float(r[i + 2]) : -INFINITY;
+                  v.w = (i + 3 < nvalid) ? __uint_as_float(r[i + 3]) : -INFINITY;
+                  dst[i >> 2] = v;
+                }
+              }
             }
           }
         } else {
@@ -432,22 +441,26 @@ ivf_threshold_kernel(const float* __restrict__ scorebuf, int64_t smax, const int
   __shared__ int hist[256];
   __shared__ uint32_t s_prefix;
   __shared__ int s_rem, s_count;
-  extern __shared__ int64_t runs[];  // [nprobe] cumulative run ends, [nprobe] list starts
+  extern __shared__ int64_t runs[];  // [nprobe] cumulative (padded) run ends, [nprobe] list starts, [nprobe] lengths
   const int q = blockIdx.x;
   const float* row = scorebuf + (size_t)q * smax;
   const int T = row_len[q];
   int64_t* run_end = runs;
   int64_t* run_x0 = runs + nprobe;
+  int64_t* run_len = runs + 2 * nprobe;
   if (threadIdx.x == 0) {
     int64_t cum = 0;
     for (int j = 0; j < nprobe; ++j) {
       const int64_t l = coarse[(size_t)q * nprobe + j];
+      int64_t len = 0;
       if (l >= 0) {
-        cum += list_off[l + 1] - list_off[l];
+        len = list_off[l + 1] - list_off[l];
         run_x0[j] = list_off[l];
       } else {
         run_x0[j] = 0;
       }
+      run_len[j] = len;
+      cum += (len + 3) & ~(int64_t)3;
       run_end[j] = cum;
     }
     s_rem = m;
@@ -463,9 +476,17 @@ ivf_threshold_kernel(const float* __restrict__ scorebuf, int64_t smax, const int
       const int shift = 24 - 8 * pass;
       for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
       __syncthreads();
-      for (int i = threadIdx.x; i < T; i += blockDim.x) {
-        const uint32_t key = f2ord(row[i]);
-        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+      // scores of one query sit in a narrow range, so most keys share a bin: aggregate equal bins inside
+      // the warp (match.any) and issue one shared-memory atomic per distinct bin
+      for (int i0 = 0; i0 < T; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        uint32_t bin = 0xFFFFFFFFu;
+        if (i < T) {
+          const uint32_t key = f2ord(row[i]);
+          if ((key & mask) == prefix) bin = (key >> shift) & 255u;
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        if (bin != 0xFFFFFFFFu && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
       }
       __syncthreads();
       if (threadIdx.x < 32) {
@@ -502,13 +523,14 @@ ivf_threshold_kernel(const float* __restrict__ scorebuf, int64_t smax, const int
   if (threadIdx.x == 0) tau[q] = t;
   for (int i = threadIdx.x; i < T; i += blockDim.x) {
     const float v = row[i];
-    if (v >= t) {
+    if (v >= t && v > -INFINITY) {
       const int slot = atomicAdd(&s_count, 1);
       if (slot < cap) {
         int j = 0;
         while (j < nprobe - 1 && i >= run_end[j]) ++j;
         const int64_t start = j > 0 ? run_end[j - 1] : 0;
         cand[(size_t)q * cap + slot] = make_uint2(__float_as_uint(v), (uint32_t)(run_x0[j] + (i - start)));
+        // (padding slots hold -inf and can only pass when t == -inf; they are filtered just below)
       }
     }
   }
@@ -829,7 +851,7 @@ IvfPlan make_ivf_plan(const b2r_index* h, int q, int k, int nprobe) {
   std::vector<int64_t> sz(h->list_sizes_host);
   std::sort(sz.begin(), sz.end(), std::greater<int64_t>());
   int64_t smax = 0;
-  for (int i = 0; i < nprobe && i < (int)sz.size(); ++i) smax += sz[i];
+  for (int i = 0; i < nprobe && i < (int)sz.size(); ++i) smax += (sz[i] + 3) & ~(int64_t)3;
   if (smax < 4) smax = 4;
   pl.smax = (int64_t)align_up((size_t)smax, 4);
   int ct = (int)llround(h->cand_factor * k);
@@ -965,7 +987,7 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     ivf_scan_kernel<<<h->num_sms, kIvfThreads, kIvfSmem, stream>>>(tmQ, h->tmX, sp);
     B2R_CHECK_LAUNCH("ivf_scan_kernel");
     }
-    ivf_threshold_kernel<<<qc, kIvfSelThreads, (size_t)np * 16, stream>>>(
+    ivf_threshold_kernel<<<qc, kIvfSelThreads, (size_t)np * 24, stream>>>(
         scorebuf, pl.smax, row_len, k, coarse, np, h->list_off, tau, count, cand, pl.cap,
         (h->rescore && !is_pq) ? qnorm : nullptr, h->maxnorm, (float)(h->scan_fp16 == 1 ? h->eps_fp16 : h->eps));
     B2R_CHECK_LAUNCH("ivf_threshold_kernel");

@@ -150,15 +150,21 @@ ivfpq_scan_kernel(const float* __restrict__ q32, int d, int m, const int64_t* __
   const int q = p / nprobe, dsub = d / m;
   for (int j = threadIdx.x; j < d; j += blockDim.x) res[j] = q32[(size_t)q * d + j] - cent[(size_t)l * d + j];
   __syncthreads();
-  // thread c computes column c of every sub-table
+  // thread c computes column c of every sub-table (128-bit loads: dsub % 4 == 0)
   {
     const int c = threadIdx.x;
+    const int d4 = dsub >> 2;
     for (int s = 0; s < m; ++s) {
-      const float* w = cb + ((size_t)s * 256 + c) * dsub;
+      const float4* w = reinterpret_cast<const float4*>(cb + ((size_t)s * 256 + c) * dsub);
+      const float4* rs = reinterpret_cast<const float4*>(res + s * dsub);
       float acc = 0.f;
-      for (int j = 0; j < dsub; ++j) {
-        const float df = res[s * dsub + j] - w[j];
-        acc = fmaf(df, df, acc);
+      for (int j = 0; j < d4; ++j) {
+        const float4 wv = __ldg(w + j);
+        const float4 rv = rs[j];
+        float df = rv.x - wv.x; acc = fmaf(df, df, acc);
+        df = rv.y - wv.y; acc = fmaf(df, df, acc);
+        df = rv.z - wv.z; acc = fmaf(df, df, acc);
+        df = rv.w - wv.w; acc = fmaf(df, df, acc);
       }
       lut[s * 256 + c] = acc;
     }
@@ -194,6 +200,9 @@ ivfpq_scan_kernel(const float* __restrict__ q32, int d, int m, const int64_t* __
     }
     out[i - x0] = -acc;
   }
+  // the run is padded to a multiple of 4 scores with -inf (runs are 16-byte aligned, see ivf.cu)
+  const int64_t len = x1 - x0, padded = (len + 3) & ~(int64_t)3;
+  if (threadIdx.x < padded - len) out[len + threadIdx.x] = -INFINITY;
 }
 
 int pq_assign(const float* r, int64_t n, int d, int m, const float* cb, uint8_t* codes, cudaStream_t stream) {

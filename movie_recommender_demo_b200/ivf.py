@@ -138,7 +138,10 @@ class IndexIVFPQ(IndexIVFFlat):
 
 def create(owner, kind):
     if kind == 'IVF':
-        return IndexIVFFlat(owner.dimension, owner.nlist, device=owner._device)
-    if kind == 'IVFPQ':
-        return IndexIVFPQ(owner.dimension, owner.nlist, owner._pq_m, device=owner._device)
-    raise ValueError(f"Unknown index type: {kind}")
+        index = IndexIVFFlat(owner.dimension, owner.nlist, device=owner._device)
+    elif kind == 'IVFPQ':
+        index = IndexIVFPQ(owner.dimension, owner.nlist, owner._pq_m, device=owner._device)
+    else:
+        raise ValueError(f"Unknown index type: {kind}")
+    index.nprobe = owner.nprobe   # the wrapper re-applies it before every search anyway (faiss_retrieval.py:150-151)
+    return index

@@ -20,6 +20,7 @@ for lo in range(0, N, 1 << 20):
     x[lo:hi] = centres[torch.randint(0, nlist, (hi - lo,), generator=g, device=dev)] + 0.35 * torch.randn((hi - lo, 256), generator=g, device=dev)
 x = torch.nn.functional.normalize(x, dim=1)
 idx = FAISSIndex(256, kind, nlist=nlist, nprobe=32, pq_m=32)
+idx.index.nprobe = 32
 idx.add(x)
 q = torch.nn.functional.normalize(centres[torch.randint(0, nlist, (Q,), generator=g, device=dev)] + 0.35 * torch.randn((Q, 256), generator=g, device=dev), dim=1)
 for _ in range(2):
