@@ -175,6 +175,7 @@ struct b2r_index {
   // ---- PQ state (kind == IVF_PQ)
   float* codebooks = nullptr;       // device [pq_m, 256, d/pq_m]
   uint8_t* codes = nullptr;         // device [capacity, pq_m] (sorted by list)
+  float* pq_list_tab = nullptr;     // device [nlist, pq_m, 256]: 2 c_ls.y_sj + |c_ls|^2 (faiss "precomputed table")
   bool pq_trained = false;
 };
 
@@ -215,6 +216,7 @@ int pq_encode(b2r_index* h, int64_t n, const float* resid, uint8_t* codes, cudaS
 int pq_scatter_codes(const uint8_t* src, const int64_t* dst, int64_t n, int m, const int32_t* list_src,
                      const int64_t* assign_src, const uint32_t* perm_src, uint32_t label0, uint8_t* ocodes,
                      int32_t* olist, uint32_t* operm, cudaStream_t stream);
-int pq_scan(b2r_index* h, int npairs, const float* q32, const int64_t* coarse, int nprobe, const int64_t* pair_out,
-            float* scorebuf, cudaStream_t stream);
+int pq_scan(b2r_index* h, int nq, int npairs, const float* q32, const int64_t* coarse, int nprobe,
+            const int64_t* pair_out, float* qtab, float* scorebuf, cudaStream_t stream);
+int pq_build_list_tables(b2r_index* h, cudaStream_t stream);
 }  // namespace b2r

@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(kIvfSelThreads)
 ivf_threshold_kernel(const float* __restrict__ scorebuf, int64_t smax, const int* __restrict__ row_len, int m,
                      const int64_t* __restrict__ coarse, int nprobe, const int64_t* __restrict__ list_off,
                      float* __restrict__ tau, int* __restrict__ cand_count, uint2* __restrict__ cand, int cap,
-                     const float* __restrict__ qnorm, const float* __restrict__ maxnorm, float eps) {
+                     const float* __restrict__ qnorm, const float* __restrict__ maxnorm, float eps, int npass) {
   __shared__ int hist[256];
   __shared__ uint32_t s_prefix;
   __shared__ int s_rem, s_count;
@@ -471,22 +471,44 @@ ivf_threshold_kernel(const float* __restrict__ scorebuf, int64_t smax, const int
   if (m >= T) {
     t = -INFINITY;
   } else {
+    // MSB-first radix select, `npass` bytes of the order-preserving key.  Stopping early leaves the low
+    // key bits zero = a LOWER bound of the k-th score (<= 2^-7 / 2^-15 relative below it): still a valid
+    // threshold (a few more candidates), one or two sweeps less over the run.
     uint32_t prefix = 0, mask = 0;
-    for (int pass = 0; pass < 4; ++pass) {
+    for (int pass = 0; pass < npass; ++pass) {
       const int shift = 24 - 8 * pass;
       for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
       __syncthreads();
-      // scores of one query sit in a narrow range, so most keys share a bin: aggregate equal bins inside
-      // the warp (match.any) and issue one shared-memory atomic per distinct bin
-      for (int i0 = 0; i0 < T; i0 += blockDim.x) {
-        const int i = i0 + threadIdx.x;
-        uint32_t bin = 0xFFFFFFFFu;
-        if (i < T) {
-          const uint32_t key = f2ord(row[i]);
-          if ((key & mask) == prefix) bin = (key >> shift) & 255u;
+      {
+        // 128-bit loads (runs are 16-byte aligned and padded to a multiple of 4), two vectors in flight
+        // per thread; run-length aggregation: a query's scores share their leading key bytes, so a
+        // thread's consecutive elements mostly hit the same bin -> one shared atomic per run
+        const float4* row4 = reinterpret_cast<const float4*>(row);
+        const int T4 = T >> 2;
+        int last = -1, run = 0;
+        auto feed = [&](float f) {
+          const uint32_t key = f2ord(f);
+          if ((key & mask) == prefix) {
+            const int b = (int)((key >> shift) & 255u);
+            if (b == last) {
+              ++run;
+            } else {
+              if (run) atomicAdd(&hist[last], run);
+              last = b;
+              run = 1;
+            }
+          }
+        };
+        for (int i = threadIdx.x; i < T4; i += 2 * blockDim.x) {
+          const float4 a = row4[i];
+          const int i2 = i + blockDim.x;
+          float4 b = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+          const bool has_b = i2 < T4;
+          if (has_b) b = row4[i2];
+          feed(a.x); feed(a.y); feed(a.z); feed(a.w);
+          if (has_b) { feed(b.x); feed(b.y); feed(b.z); feed(b.w); }
         }
-        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
-        if (bin != 0xFFFFFFFFu && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
+        if (run) atomicAdd(&hist[last], run);
       }
       __syncthreads();
       if (threadIdx.x < 32) {
@@ -521,17 +543,23 @@ ivf_threshold_kernel(const float* __restrict__ scorebuf, int64_t smax, const int
     if (qnorm) t -= rescore_margin(eps, qnorm[q], *maxnorm);   // candidates = the provable rescore window
   }
   if (threadIdx.x == 0) tau[q] = t;
-  for (int i = threadIdx.x; i < T; i += blockDim.x) {
-    const float v = row[i];
-    if (v >= t && v > -INFINITY) {
-      const int slot = atomicAdd(&s_count, 1);
-      if (slot < cap) {
-        int j = 0;
-        while (j < nprobe - 1 && i >= run_end[j]) ++j;
-        const int64_t start = j > 0 ? run_end[j - 1] : 0;
-        cand[(size_t)q * cap + slot] = make_uint2(__float_as_uint(v), (uint32_t)(run_x0[j] + (i - start)));
-        // (padding slots hold -inf and can only pass when t == -inf; they are filtered just below)
+  {
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    const int T4 = T >> 2;
+    auto emit = [&](float v, int i) {
+      if (v >= t && v > -INFINITY) {
+        const int slot = atomicAdd(&s_count, 1);
+        if (slot < cap) {
+          int j = 0;
+          while (j < nprobe - 1 && i >= run_end[j]) ++j;
+          const int64_t start = j > 0 ? run_end[j - 1] : 0;
+          cand[(size_t)q * cap + slot] = make_uint2(__float_as_uint(v), (uint32_t)(run_x0[j] + (i - start)));
+        }
       }
+    };
+    for (int i = threadIdx.x; i < T4; i += blockDim.x) {
+      const float4 a = row4[i];
+      emit(a.x, 4 * i); emit(a.y, 4 * i + 1); emit(a.z, 4 * i + 2); emit(a.w, 4 * i + 3);
     }
   }
   __syncthreads();
@@ -605,7 +633,7 @@ int set_centroids(b2r_index* h, const float* cent_dev, cudaStream_t stream) {
   }
   h->list_sizes_host.assign(h->nlist, 0);
   h->trained = (h->kind != B2R_KIND_IVF_PQ) || h->pq_trained;
-  return B2R_OK;
+  return pq_build_list_tables(h, stream);   // no-op unless this is an IVF-PQ index with codebooks
 }
 
 }  // namespace
@@ -616,6 +644,7 @@ void ivf_free(b2r_index* h) {
   cudaFree(h->perm);
   cudaFree(h->codebooks);
   cudaFree(h->codes);
+  cudaFree(h->pq_list_tab);
   h->list_off = nullptr;
 }
 
@@ -839,7 +868,7 @@ struct IvfPlan {
   int64_t smax = 0, pairs_pad = 0;
   size_t off_q16, off_q32, off_qnorm, off_coarse, off_cdist, off_pair_out, off_row_len, off_listcnt, off_pairoff,
       off_cursor, off_pair_sorted, off_gq16, off_units, off_nunits, off_tau, off_count, off_cand, off_score,
-      off_qws, qws_bytes, total;
+      off_qws, off_qtab, qws_bytes, total;
 };
 
 IvfPlan make_ivf_plan(const b2r_index* h, int q, int k, int nprobe) {
@@ -859,7 +888,7 @@ IvfPlan make_ivf_plan(const b2r_index* h, int q, int k, int nprobe) {
   if (ct > 2560) ct = 2560;
   if (ct < k) ct = k;
   pl.c_target = ct;
-  const int64_t budget = (int64_t)2 << 30;
+  const int64_t budget = (int64_t)6 << 30;   // score runs of one query chunk (fewer chunks = fewer passes over the lists)
   int64_t qc = budget / (pl.smax * 4);
   if (qc < 1) qc = 1;
   if (qc > 8192) qc = 8192;
@@ -895,6 +924,7 @@ IvfPlan make_ivf_plan(const b2r_index* h, int q, int k, int nprobe) {
   pl.off_score = take((size_t)pl.chunk * pl.smax * 4);
   pl.qws_bytes = flat_search_workspace(h->quantizer, pl.chunk, nprobe);
   pl.off_qws = take(pl.qws_bytes);
+  pl.off_qtab = take(h->kind == B2R_KIND_IVF_PQ ? (size_t)pl.chunk * h->pq_m * 256 * 4 : 0);
   pl.total = off;
   return pl;
 }
@@ -963,7 +993,9 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     B2R_CHECK_LAUNCH("pair_runs_kernel");
     if (is_pq) {
       // ADC scan: one CTA per (query, probed list) pair, LUT in shared memory (ivfpq.cu)
-      if ((rc = pq_scan(h, npairs, q32, coarse, np, pair_out, scorebuf, stream))) return rc;
+      if ((rc = pq_scan(h, qc, npairs, q32, coarse, np, pair_out, reinterpret_cast<float*>(ws + pl.off_qtab), scorebuf,
+                        stream)))
+        return rc;
     } else {
     scan_lists_kernel<<<1, 1024, 0, stream>>>(listcnt, nullptr, h->nlist, pairoff, cursor);
     B2R_CHECK_LAUNCH("scan_lists_kernel(pairs)");
@@ -989,7 +1021,8 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     }
     ivf_threshold_kernel<<<qc, kIvfSelThreads, (size_t)np * 24, stream>>>(
         scorebuf, pl.smax, row_len, k, coarse, np, h->list_off, tau, count, cand, pl.cap,
-        (h->rescore && !is_pq) ? qnorm : nullptr, h->maxnorm, (float)(h->scan_fp16 == 1 ? h->eps_fp16 : h->eps));
+        (h->rescore && !is_pq) ? qnorm : nullptr, h->maxnorm, (float)(h->scan_fp16 == 1 ? h->eps_fp16 : h->eps),
+        is_pq ? 4 : 3);   // IVF-Flat re-scores the window, a 2^-15-relative lower bound suffices; PQ needs the exact k-th
     B2R_CHECK_LAUNCH("ivf_threshold_kernel");
     SelectParams sel;
     memset(&sel, 0, sizeof(sel));

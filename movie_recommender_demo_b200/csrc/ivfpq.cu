@@ -134,39 +134,84 @@ __global__ void scatter_codes_kernel(const uint8_t* __restrict__ src, const int6
 }
 
 // ------------------------------------------------------------------ ADC scan ---
-// One CTA per (query, probe slot) pair: table in shared memory, then the list's codes.
-// Writes NEGATED distances (so that "larger is better" like the inner-product paths).
+// |(q - c_l)_s - y_sj|^2 = |q_s - y_sj|^2  +  (2 c_ls.y_sj + |c_ls|^2)  -  2 c_ls.q_s
+//                          A[q][s][j]          B[l][s][j]                  bias[s] (per pair)
+// A is built once per query, B once per list (at training / import time); a (query, list) pair only
+// adds the two 32 KB tables instead of re-reading the whole codebook (faiss's "precomputed table").
+
+// B[l][s][j]: one CTA per list, thread j
+__global__ void __launch_bounds__(256)
+pq_list_tables_kernel(const float* __restrict__ cent, const float* __restrict__ cb, int d, int m,
+                      float* __restrict__ B) {
+  const int l = blockIdx.x, j = threadIdx.x, dsub = d / m, d4 = dsub >> 2;
+  for (int s = 0; s < m; ++s) {
+    const float4* w = reinterpret_cast<const float4*>(cb + ((size_t)s * 256 + j) * dsub);
+    const float4* c = reinterpret_cast<const float4*>(cent + (size_t)l * d + s * dsub);
+    float dot = 0.f, nn = 0.f;
+    for (int t = 0; t < d4; ++t) {
+      const float4 wv = __ldg(w + t), cv = __ldg(c + t);
+      dot = fmaf(cv.x, wv.x, dot); dot = fmaf(cv.y, wv.y, dot); dot = fmaf(cv.z, wv.z, dot); dot = fmaf(cv.w, wv.w, dot);
+      nn = fmaf(cv.x, cv.x, nn); nn = fmaf(cv.y, cv.y, nn); nn = fmaf(cv.z, cv.z, nn); nn = fmaf(cv.w, cv.w, nn);
+    }
+    B[((size_t)l * m + s) * 256 + j] = 2.0f * dot + nn;
+  }
+}
+
+// A[q][s][j]: one CTA per query, thread j
+__global__ void __launch_bounds__(256)
+pq_query_tables_kernel(const float* __restrict__ q32, const float* __restrict__ cb, int d, int m,
+                       float* __restrict__ A) {
+  extern __shared__ float qs[];
+  const int q = blockIdx.x, j = threadIdx.x, dsub = d / m, d4 = dsub >> 2;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) qs[i] = q32[(size_t)q * d + i];
+  __syncthreads();
+  for (int s = 0; s < m; ++s) {
+    const float4* w = reinterpret_cast<const float4*>(cb + ((size_t)s * 256 + j) * dsub);
+    const float4* qv = reinterpret_cast<const float4*>(qs + s * dsub);
+    float acc = 0.f;
+    for (int t = 0; t < d4; ++t) {
+      const float4 wv = __ldg(w + t), rv = qv[t];
+      float df = rv.x - wv.x; acc = fmaf(df, df, acc);
+      df = rv.y - wv.y; acc = fmaf(df, df, acc);
+      df = rv.z - wv.z; acc = fmaf(df, df, acc);
+      df = rv.w - wv.w; acc = fmaf(df, df, acc);
+    }
+    A[((size_t)q * m + s) * 256 + j] = acc;
+  }
+}
+
+// One CTA per (query, probe slot) pair: LUT = A[q] + B[l] + bias in shared memory, then the list's
+// codes (128-bit loads, m shared-memory look-ups per row).  Writes NEGATED distances so that
+// "larger is better" like the inner-product paths.
 __global__ void __launch_bounds__(256)
 ivfpq_scan_kernel(const float* __restrict__ q32, int d, int m, const int64_t* __restrict__ coarse, int nprobe,
-                  const float* __restrict__ cent, const float* __restrict__ cb, const int64_t* __restrict__ list_off,
-                  const uint8_t* __restrict__ codes, const int64_t* __restrict__ pair_out,
-                  float* __restrict__ scorebuf) {
+                  const float* __restrict__ cent, const float* __restrict__ A, const float* __restrict__ B,
+                  const int64_t* __restrict__ list_off, const uint8_t* __restrict__ codes,
+                  const int64_t* __restrict__ pair_out, float* __restrict__ scorebuf) {
   extern __shared__ float sm[];
   float* lut = sm;              // [m, 256]
-  float* res = sm + m * 256;    // [d] residual q - c
+  float* bias = sm + m * 256;   // [m]
   const int p = blockIdx.x;
   const int64_t l = coarse[p];
   if (l < 0) return;
   const int q = p / nprobe, dsub = d / m;
-  for (int j = threadIdx.x; j < d; j += blockDim.x) res[j] = q32[(size_t)q * d + j] - cent[(size_t)l * d + j];
+  if (threadIdx.x < m) {
+    const int s = threadIdx.x;
+    const float* qv = q32 + (size_t)q * d + s * dsub;
+    const float* cv = cent + (size_t)l * d + s * dsub;
+    float dot = 0.f;
+    for (int t = 0; t < dsub; ++t) dot = fmaf(cv[t], qv[t], dot);
+    bias[s] = -2.0f * dot;
+  }
   __syncthreads();
-  // thread c computes column c of every sub-table (128-bit loads: dsub % 4 == 0)
   {
-    const int c = threadIdx.x;
-    const int d4 = dsub >> 2;
-    for (int s = 0; s < m; ++s) {
-      const float4* w = reinterpret_cast<const float4*>(cb + ((size_t)s * 256 + c) * dsub);
-      const float4* rs = reinterpret_cast<const float4*>(res + s * dsub);
-      float acc = 0.f;
-      for (int j = 0; j < d4; ++j) {
-        const float4 wv = __ldg(w + j);
-        const float4 rv = rs[j];
-        float df = rv.x - wv.x; acc = fmaf(df, df, acc);
-        df = rv.y - wv.y; acc = fmaf(df, df, acc);
-        df = rv.z - wv.z; acc = fmaf(df, df, acc);
-        df = rv.w - wv.w; acc = fmaf(df, df, acc);
-      }
-      lut[s * 256 + c] = acc;
+    const float4* a4 = reinterpret_cast<const float4*>(A + (size_t)q * m * 256);
+    const float4* b4 = reinterpret_cast<const float4*>(B + (size_t)l * m * 256);
+    float4* l4 = reinterpret_cast<float4*>(lut);
+    for (int i = threadIdx.x; i < m * 64; i += blockDim.x) {
+      const float4 av = __ldg(a4 + i), bv = __ldg(b4 + i);
+      const float bs = bias[i >> 6];
+      l4[i] = make_float4(av.x + bv.x + bs, av.y + bv.y + bs, av.z + bv.z + bs, av.w + bv.w + bs);
     }
   }
   __syncthreads();
@@ -262,7 +307,7 @@ int pq_train(b2r_index* h, int64_t n, const float* resid, uint64_t seed, cudaStr
     B2R_CHECK_LAUNCH("pq_finalize_kernel");
   }
   h->pq_trained = true;
-  return B2R_OK;
+  return pq_build_list_tables(h, stream);
 }
 
 int pq_encode(b2r_index* h, int64_t n, const float* resid, uint8_t* codes, cudaStream_t stream) {
@@ -279,18 +324,33 @@ int pq_scatter_codes(const uint8_t* src, const int64_t* dst, int64_t n, int m, c
   return B2R_OK;
 }
 
-int pq_scan(b2r_index* h, int npairs, const float* q32, const int64_t* coarse, int nprobe, const int64_t* pair_out,
-            float* scorebuf, cudaStream_t stream) {
+int pq_build_list_tables(b2r_index* h, cudaStream_t stream) {
+  if (h->kind != B2R_KIND_IVF_PQ || !h->pq_trained || !h->quantizer || h->quantizer->ntotal != h->nlist) return B2R_OK;
+  const size_t bytes = (size_t)h->nlist * h->pq_m * 256 * 4;
+  if (!h->pq_list_tab && cudaMalloc(&h->pq_list_tab, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(B2R_ENOMEM, "cudaMalloc of the PQ per-list tables (" + std::to_string(bytes) + " bytes) failed");
+  }
+  pq_list_tables_kernel<<<h->nlist, 256, 0, stream>>>(h->quantizer->x32, h->codebooks, h->d, h->pq_m, h->pq_list_tab);
+  B2R_CHECK_LAUNCH("pq_list_tables_kernel");
+  return B2R_OK;
+}
+
+int pq_scan(b2r_index* h, int nq, int npairs, const float* q32, const int64_t* coarse, int nprobe,
+            const int64_t* pair_out, float* qtab, float* scorebuf, cudaStream_t stream) {
   const int d = h->d, m = h->pq_m;
-  const size_t smem = (size_t)m * 256 * 4 + (size_t)d * 4;
+  if (!h->pq_list_tab) return fail(B2R_ESTATE, "IVF-PQ per-list tables are missing");
+  pq_query_tables_kernel<<<nq, 256, (size_t)d * 4, stream>>>(q32, h->codebooks, d, m, qtab);
+  B2R_CHECK_LAUNCH("pq_query_tables_kernel");
+  const size_t smem = (size_t)m * 256 * 4 + (size_t)m * 4;
   static bool configured[64] = {};
   int dev = 0;
   B2R_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
-    B2R_CUDA(cudaFuncSetAttribute(ivfpq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 256 * 4 + 1024 * 4));
+    B2R_CUDA(cudaFuncSetAttribute(ivfpq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 256 * 4 + 256));
     configured[dev & 63] = true;
   }
-  ivfpq_scan_kernel<<<npairs, 256, smem, stream>>>(q32, d, m, coarse, nprobe, h->quantizer->x32, h->codebooks,
+  ivfpq_scan_kernel<<<npairs, 256, smem, stream>>>(q32, d, m, coarse, nprobe, h->quantizer->x32, qtab, h->pq_list_tab,
                                                    h->list_off, h->codes, pair_out, scorebuf);
   B2R_CHECK_LAUNCH("ivfpq_scan_kernel");
   return B2R_OK;
@@ -321,6 +381,9 @@ int b2r_index_import_codebooks(b2r_index* h, const float* in) {
   B2R_CUDA(cudaMemcpy(h->codebooks, in, bytes, cudaMemcpyHostToDevice));
   h->pq_trained = true;
   h->trained = h->quantizer && h->quantizer->ntotal == h->nlist;
+  int rc = pq_build_list_tables(h, 0);
+  if (rc) return rc;
+  B2R_CUDA(cudaStreamSynchronize(0));
   return B2R_OK;
 }
 

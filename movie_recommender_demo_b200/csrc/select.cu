@@ -136,17 +136,24 @@ kth_value_kernel(const float* __restrict__ vals, int64_t T, int64_t ld, int m, f
       const int shift = 24 - 8 * pass;
       for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
       __syncthreads();
-      // keys of one row share most of their leading bits: aggregate equal bins inside the warp
-      // (match.any) so a bin costs one shared-memory atomic per warp instead of one per lane
-      for (int64_t i0 = 0; i0 < T; i0 += blockDim.x) {
-        const int64_t i = i0 + threadIdx.x;
-        uint32_t bin = 0xFFFFFFFFu;
-        if (i < T) {
+      {
+        // run-length aggregation: the scores of one query share their leading key bytes, so a thread's
+        // consecutive elements mostly hit the same bin -> one shared-memory atomic per run, not per element
+        int last = -1, run = 0;
+        for (int64_t i = threadIdx.x; i < T; i += blockDim.x) {
           const uint32_t key = f2ord(row[i]);
-          if ((key & mask) == prefix) bin = (key >> shift) & 255u;
+          if ((key & mask) == prefix) {
+            const int b = (int)((key >> shift) & 255u);
+            if (b == last) {
+              ++run;
+            } else {
+              if (run) atomicAdd(&hist[last], run);
+              last = b;
+              run = 1;
+            }
+          }
         }
-        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
-        if (bin != 0xFFFFFFFFu && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
+        if (run) atomicAdd(&hist[last], run);
       }
       __syncthreads();
       if (threadIdx.x < 32) radix_pick_bin(hist, &s_rem, &s_prefix, prefix, shift);
