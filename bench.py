@@ -268,7 +268,8 @@ def run_b200(args):
     # ---- warm-up (also exercises the e2e path once)
     for _ in range(max(args.warmup, 3)):
         _, _, st = device_step(q_dev)
-    e2e_step()
+    if not args.no_e2e:
+        e2e_step()
     barrier()
     status_bad = int((st != 0).sum().item())
 
@@ -316,22 +317,25 @@ def run_b200(args):
                  "kernel_ms": scan_ms, "traffic": _traffic_note(Q) if shard_rows == CORPUS_1GPU else None})
 
     # ---- timed: e2e through the public API with host buffers
-    barrier()
-    w0 = time.time()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = e2e_step()
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-    windows.append((w0, time.time()))
-    e2e_value = args.steps * Q / (e2e_ms / 1e3)
+    e2e_value = e2e_ms = None
+    res = None
+    if not args.no_e2e:
+        barrier()
+        w0 = time.time()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = e2e_step()
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        windows.append((w0, time.time()))
+        e2e_value = args.steps * Q / (e2e_ms / 1e3)
 
     clocks = sampler.stop(windows) if sampler else None
 
     # ---- CPU baseline + parity spot check (rank 0, single GPU only)
     cpu = None
     parity = None
-    if world == 1 and rank == 0 and not args.no_cpu:
+    if world == 1 and rank == 0 and not args.no_cpu and res is not None:
         from oracle.compare import compare_topk
         x_host = index.index.reconstruct_n(0, total_rows).cpu().numpy()
         search = cpu_search_fn(x_host, index.id_map)
@@ -372,7 +376,7 @@ def run_b200(args):
                 "l2_policy": "no flush: corpus (bf16 scan copy + fp32 master) is larger than the 126 MB L2",
                 "corpus_build_s": round(t_build, 2),
             },
-            "e2e": {"value": e2e_value, "unit": "queries/s", "ms_per_step": e2e_ms / args.steps,
+            "e2e": None if e2e_value is None else {"value": e2e_value, "unit": "queries/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * K_TOP * 12 + Q * 4},
             "gpu_launches": launches,
             "roofline": roof,
@@ -408,6 +412,7 @@ def main():
     ap.add_argument("--corpus-rows", type=int, default=0, help="override total corpus rows")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer (e2e) leg: profiling runs only")
     ap.add_argument("--scan-dtype", choices=["auto", "bf16", "fp16"], default="auto",
                     help="16-bit format of the scan copy (auto = fp16 for L2-normalised corpora)")
     args = ap.parse_args()

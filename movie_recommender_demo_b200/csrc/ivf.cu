@@ -29,7 +29,8 @@ namespace {
 
 constexpr int kKmeansIters = 10;          // faiss ClusteringParameters.niter
 constexpr int kMaxPointsPerCentroid = 256;  // faiss ClusteringParameters.max_points_per_centroid
-constexpr int kUnitTiles = 8;             // corpus tiles (of 128 rows) per scan unit
+constexpr int kUnitTilesSmallQ = 8;       // corpus tiles (of 128 rows) per scan unit: few queries -> split lists for parallelism
+constexpr int kUnitTilesLargeQ = 64;      // many queries -> whole lists per unit (one query-block load per list, fewer pipeline drains)
 
 // ------------------------------------------------------------------ small kernels ---
 __global__ void gather_rows_f32_kernel(const float* __restrict__ src, const int64_t* __restrict__ rows,
@@ -225,7 +226,7 @@ struct IvfUnit {
 
 __global__ void build_units_kernel(const int64_t* __restrict__ list_off, const int64_t* __restrict__ pair_off,
                                    int nlist, IvfUnit* __restrict__ units, int* __restrict__ num_units,
-                                   int max_units) {
+                                   int max_units, int kUnitTiles) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= nlist) return;
   const int64_t q0 = pair_off[l], q1 = pair_off[l + 1];
@@ -899,7 +900,7 @@ IvfPlan make_ivf_plan(const b2r_index* h, int q, int k, int nprobe) {
   // units <= sum over lists ceil(nq/128) * ceil(tiles/8); bound: (pairs/128 + nlist) query blocks,
   // each with <= ceil(max_list_tiles / 8) tile chunks
   const int64_t max_tiles = sz.empty() ? 1 : ceil_div(sz[0] > 0 ? sz[0] : 1, kTileRows);
-  int64_t mu = (pairs / kQBlock + std::min<int64_t>(h->nlist, pairs) + 1) * ceil_div(max_tiles, kUnitTiles);
+  int64_t mu = (pairs / kQBlock + std::min<int64_t>(h->nlist, pairs) + 1) * ceil_div(max_tiles, kUnitTilesSmallQ);
   if (mu > (1 << 24)) mu = 1 << 24;
   pl.max_units = (int)mu;
   size_t off = 0;
@@ -1002,8 +1003,8 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     scatter_pairs_kernel<<<(unsigned)ceil_div(npairs, 8), 256, 0, stream>>>(
         coarse, npairs, np, reinterpret_cast<unsigned long long*>(cursor), pair_sorted, q16, d, gq16);
     B2R_CHECK_LAUNCH("scatter_pairs_kernel");
-    build_units_kernel<<<(unsigned)ceil_div(h->nlist, 128), 128, 0, stream>>>(h->list_off, pairoff, h->nlist, units,
-                                                                              nunits, pl.max_units);
+    build_units_kernel<<<(unsigned)ceil_div(h->nlist, 128), 128, 0, stream>>>(
+        h->list_off, pairoff, h->nlist, units, nunits, pl.max_units, qc >= 512 ? kUnitTilesLargeQ : kUnitTilesSmallQ);
     B2R_CHECK_LAUNCH("build_units_kernel");
     CUtensorMap tmQ;
     if ((rc = make_tmap_bf16_rows(&tmQ, gq16, pl.pairs_pad, d))) return rc;
