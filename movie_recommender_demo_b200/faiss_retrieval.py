@@ -446,10 +446,26 @@ class FAISSIndex:
         return np.vstack(ids_parts), np.vstack(dist_parts)
 
     # ------------------------------------------------------------ save/load
-    def save(self, filepath: str) -> None:
-        """Index file (native container) + the reference's pickled `.metadata` side-car
-        (same keys as faiss_retrieval.py:209-219)."""
+    def save(self, filepath: str, *, format: str = "faiss") -> None:
+        """Index file + the reference's pickled `.metadata` side-car (same keys as
+        faiss_retrieval.py:209-219).  `format="faiss"` (default) writes the `faiss.write_index` layout
+        (faiss_io.py) so the file is interchangeable with the reference's; `format="native"` writes
+        this package's own container."""
         Path(filepath).parent.mkdir(parents=True, exist_ok=True)
+        if format == "faiss":
+            from . import faiss_io
+            self.index.nprobe = self.nprobe
+            faiss_io.write_index(self.index, filepath)
+        elif format == "native":
+            self._save_native(filepath)
+        else:
+            raise ValueError(f"unknown index file format {format!r}")
+        with open(filepath + '.metadata', 'wb') as f:
+            pickle.dump({'dimension': self.dimension, 'index_type': self.index_type, 'nlist': self.nlist,
+                         'nprobe': self.nprobe, 'id_map': list(self.id_map)}, f)
+        self._say(f"Index saved to {filepath}")
+
+    def _save_native(self, filepath: str) -> None:
         state = self.index.state_dict() if hasattr(self.index, "state_dict") else {}
         n = self.index.ntotal
         if n and getattr(self.index, "stores_vectors", True):
@@ -463,23 +479,40 @@ class FAISSIndex:
             f.write(struct.pack("<Q", len(blob)))
             f.write(blob)
             f.write(vecs.astype(np.float32, copy=False).tobytes())
-        with open(filepath + '.metadata', 'wb') as f:
-            pickle.dump({'dimension': self.dimension, 'index_type': self.index_type, 'nlist': self.nlist,
-                         'nprobe': self.nprobe, 'id_map': list(self.id_map)}, f)
-        self._say(f"Index saved to {filepath}")
 
     def load(self, filepath: str) -> None:
+        """Reads either layout (sniffed from the first bytes): a `faiss.write_index` file of the
+        reference (Flat / IVFFlat / IVFPQ) or this package's native container."""
+        from . import faiss_io
         with open(filepath + '.metadata', 'rb') as f:
             meta = pickle.load(f)
         self.dimension = meta['dimension']
         self.index_type = meta['index_type']
         self.nlist = meta['nlist']
         self.nprobe = meta['nprobe']
+        layout = faiss_io.sniff(filepath)
+        if layout == "faiss":
+            index = faiss_io.read_index(filepath, device=self._device)
+            want = {'Flat': 'IndexFlatIP', 'IVF': 'IndexIVFFlat', 'IVFPQ': 'IndexIVFPQ'}.get(self.index_type)
+            if type(index).__name__ != want:
+                raise ValueError(f"{filepath}: holds a {type(index).__name__}, metadata says {self.index_type}")
+            if index.d != self.dimension:
+                raise ValueError(f"{filepath}: dimension {index.d} != metadata dimension {self.dimension}")
+            self.index = index
+            self._pq_m = getattr(index, "pq_m", self._pq_m)
+        elif layout == "native":
+            self._load_native(filepath)
+        else:
+            raise ValueError(f"{filepath}: neither a faiss index file (IxFI/IwFl/IwPQ) nor a b200 native container")
+        self.id_map = list(meta['id_map'])
+        self._ids_all_int = all(isinstance(a, (int, np.integer)) for a in self.id_map)
+        self._sync_ids()
+        self._say(f"Index loaded from {filepath}")
+        self._say(f"Index size: {self.index.ntotal}")
+
+    def _load_native(self, filepath: str) -> None:
         with open(filepath, "rb") as f:
-            magic = f.read(8)
-            if magic != _NATIVE_MAGIC:
-                raise ValueError(f"{filepath}: not a b200 index file (faiss-format import is not available "
-                                 "in this build)")
+            f.read(8)
             (blen,) = struct.unpack("<Q", f.read(8))
             head = pickle.loads(f.read(blen))
             vecs = np.frombuffer(f.read(), dtype=np.float32).reshape(head["ntotal"], head["dimension"])
@@ -493,11 +526,6 @@ class FAISSIndex:
             self.index.load_state_dict(head["state"])
         if len(vecs):
             self.index.add(vecs, normalize=False)  # stored rows are already normalised
-        self.id_map = list(meta['id_map'])
-        self._ids_all_int = all(isinstance(a, (int, np.integer)) for a in self.id_map)
-        self._sync_ids()
-        self._say(f"Index loaded from {filepath}")
-        self._say(f"Index size: {self.index.ntotal}")
 
     def get_stats(self) -> Dict:
         return {

@@ -50,6 +50,19 @@ class IndexIVFFlat(_DeviceIndex):
         _lib.check(self._lib.b2r_index_list_sizes(self._h, out.ctypes.data))
         return out
 
+    def lists_by_label(self) -> np.ndarray:
+        """int64 [ntotal] inverted-list id of every vector, in insertion (label) order."""
+        torch = self._torch
+        n = self.ntotal
+        stored = np.repeat(np.arange(self.nlist, dtype=np.int64), self.list_sizes())   # rows are sorted by list
+        with torch.cuda.device(self.device):
+            labels = torch.empty(n, dtype=torch.int64, device=self.device)
+            _lib.check(self._lib.b2r_index_get_labels(self._h, 0, n, labels.data_ptr(),
+                                                      int(torch.cuda.current_stream(self.device).cuda_stream)))
+        out = np.empty(n, dtype=np.int64)
+        out[labels.cpu().numpy()] = stored
+        return out
+
     def state_dict(self) -> dict:
         return {"centroids": self.export_centroids()} if self.is_trained else {}
 
@@ -93,19 +106,6 @@ class IndexIVFPQ(IndexIVFFlat):
 
     def reconstruct_n(self, i0: int, n: int):
         raise NotImplementedError("IVF-PQ stores codes only")
-
-    def lists_by_label(self) -> np.ndarray:
-        """int64 [ntotal] inverted-list id of every vector, in insertion (label) order."""
-        torch = self._torch
-        n = self.ntotal
-        stored = np.repeat(np.arange(self.nlist, dtype=np.int64), self.list_sizes())   # rows are sorted by list
-        with torch.cuda.device(self.device):
-            labels = torch.empty(n, dtype=torch.int64, device=self.device)
-            _lib.check(self._lib.b2r_index_get_labels(self._h, 0, n, labels.data_ptr(),
-                                                      int(torch.cuda.current_stream(self.device).cuda_stream)))
-        out = np.empty(n, dtype=np.int64)
-        out[labels.cpu().numpy()] = stored
-        return out
 
     def add_codes(self, codes, lists) -> None:
         torch = self._torch
