@@ -278,13 +278,16 @@ select_rescore_kernel(const SelectParams p) {
     }
     __syncthreads();
     const int lane = tid & 31;
+    // without a rescore (IVF-PQ) the scan score is final: key on the LABEL right away, so that the
+    // selection below is canonical (score desc, label asc) even among exact ties
+    const uint32_t* to_label = p.rescore ? nullptr : p.perm;
     for (int sgi = tid >> 5; sgi < p.nseg; sgi += (blockDim.x >> 5)) {
       const int pos0 = soff[sgi], n = soff[sgi + 1] - pos0;
       const uint2* seg = p.cand + ((size_t)q * p.nseg + sgi) * p.cap_seg;
       for (int i = lane; i < n; i += 32) {
         if (pos0 + i < kKeyCap) {
           const uint2 e = seg[i];
-          keys[pos0 + i] = make_key(__uint_as_float(e.x), e.y);
+          keys[pos0 + i] = make_key(__uint_as_float(e.x), to_label ? to_label[e.y] : e.y);
         }
       }
     }
@@ -339,8 +342,9 @@ select_rescore_kernel(const SelectParams p) {
   __syncthreads();
   int R = s_R;
   if (R > kRescoreMax) {
-    // window larger than the buffer: keep the best kRescoreMax by bf16 score (not provably exact)
-    status |= B2R_ST_RESCORE_OVERFLOW;
+    // window larger than the buffer: keep the best kRescoreMax by scan score.  With a rescore that is
+    // not provably exact; without one (keys already final) the best kRescoreMax >= k are the answer.
+    if (p.rescore) status |= B2R_ST_RESCORE_OVERFLOW;
     __syncthreads();
     const int P = next_pow2(c > 1 ? c : 1);
     for (int i = c + tid; i < P; i += blockDim.x) keys[i] = 0;
@@ -386,12 +390,6 @@ select_rescore_kernel(const SelectParams p) {
         const uint32_t ix = lane == 0 ? idx[0] : lane == 1 ? idx[1] : lane == 2 ? idx[2] : idx[3];
         rkeys[i0 + lane] = make_key(a, p.perm ? p.perm[ix] : ix);   // final order is by label
       }
-    }
-  } else if (p.perm) {
-    __syncthreads();
-    for (int i = tid; i < R; i += blockDim.x) {
-      const uint64_t key = rkeys[i];
-      rkeys[i] = (key & 0xFFFFFFFF00000000ull) | (uint64_t)(0xFFFFFFFFu - p.perm[key_idx(key)]);
     }
   }
   const int R2 = next_pow2(R > 1 ? R : 1);

@@ -111,6 +111,11 @@ class _DeviceIndex:
         if a.ndim != 2 or a.shape[1] != self.d:
             raise ValueError(f"{what}: expected shape [n, {self.d}], got {a.shape}")
         a = np.ascontiguousarray(a, dtype=np.float32)
+        if not a.flags.writeable:       # read-only views (np.frombuffer, memmap): torch wants a writable source
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", UserWarning)
+                return torch.from_numpy(a).to(self.device, non_blocking=False)
         return torch.from_numpy(a).to(self.device, non_blocking=False)
 
     def _workspace(self, nbytes: int):

@@ -106,7 +106,7 @@ def test_host_authored_ivf_file_answers_like_the_oracle(fr, tmp_path):
 
 
 def test_load_rejects_mismatched_metadata(fr, tmp_path):
-    d = 32
+    d = 64
     g = fr.FAISSIndex(d, 'Flat')
     g.add(_clustered(500, d, 4, seed=1))
     path = str(tmp_path / "f.index")

@@ -75,3 +75,25 @@ def test_ivfpq_reference_defaults_and_save_load(fr, tmp_path):
     assert h.index_type == 'IVFPQ' and h.index.ntotal == 20000
     ids2, dist2 = h.search(q, k=100)
     assert np.array_equal(ids, ids2) and np.allclose(dist, dist2)
+
+
+def test_ivfpq_exact_ties_are_ordered_by_label(fr):
+    """The reference trains on the RAW input and adds the normalised rows (faiss_retrieval.py:107-118), so
+    with large-norm input every row of a list gets the same PQ code -> hundreds of exact ADC ties.  The
+    answer must then be canonical: distance ascending, label ascending inside a tie, no 'inexact' flag."""
+    import warnings
+    d, N = 64, 12000
+    x = _clustered(N, d, 40, seed=3) * np.float32(8.0)       # large-norm input: the quirk's worst case
+    q = _clustered(9, d, 40, seed=4)
+    g = fr.FAISSIndex(d, 'IVFPQ', nlist=20, nprobe=5)
+    g.add(x)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")                       # a status warning would fail the test
+        ids, dist = g.search(q, k=60)
+        ids2, dist2 = g.search(q, k=600)
+    for I, D in ((ids, dist), (ids2, dist2)):
+        assert (np.diff(D, axis=1) >= 0).all()
+        same = np.diff(D, axis=1) == 0
+        assert same.mean() > 0.3, "this configuration is supposed to be tie-heavy"
+        assert (np.diff(I, axis=1)[same] > 0).all(), "ties must be ordered by label"
+    assert np.array_equal(ids, ids2[:, :60])
