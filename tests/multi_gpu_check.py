@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 
 from movie_recommender_demo_b200.faiss_retrieval import IndexFlatIP
-from movie_recommender_demo_b200.sharded import ShardedFlatIndex
+from movie_recommender_demo_b200.sharded import ShardedFlatIndex, ShardedIVFIndex
 
 N, D, Q, K, CHUNK = 2_000_000, 256, 96, 500, 1 << 18
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -45,6 +45,44 @@ if rank == 0:
     ok = same_ids and same_d and int((st != 0).sum()) == 0
     print(f"multi_gpu_check world={world}: ids identical={same_ids} scores identical={same_d} "
           f"status_nonzero={int((st != 0).sum())} -> {'PASS' if ok else 'FAIL'}")
+
+# ---- IVF-Flat and IVF-PQ: replicated quantisers, row-sharded lists ----------------
+from movie_recommender_demo_b200 import ivf  # noqa: E402
+
+NI, NLIST, NPROBE = 1_000_000, 256, 16
+
+
+def unit_chunk(c):
+    x = chunk(c)
+    return x / x.norm(dim=1, keepdim=True)
+
+
+for kind in ("IVF", "IVFPQ"):
+    shi = ShardedIVFIndex(D, NI, NLIST, nprobe=NPROBE, kind=kind, pq_m=32, device=local)
+    shi.train(unit_chunk(0) if rank == 0 else None)          # collective: rank 0 trains, quantisers broadcast
+    for c in range(shi.lo // CHUNK, (shi.hi - 1) // CHUNK + 1):
+        rows = unit_chunk(c)
+        shi.add_local(rows[max(shi.lo, c * CHUNK) - c * CHUNK: min(shi.hi, (c + 1) * CHUNK) - c * CHUNK])
+    Dm, Im, st = shi.search_device(q, K)
+    torch.cuda.synchronize()
+    if rank == 0:
+        if kind == "IVF":
+            full = ivf.IndexIVFFlat(D, NLIST, device=local)
+        else:
+            full = ivf.IndexIVFPQ(D, NLIST, 32, device=local)
+            full.import_codebooks(shi.local.export_codebooks())
+        full.import_centroids(shi.local.export_centroids())
+        for c in range((NI + CHUNK - 1) // CHUNK):
+            full.add(unit_chunk(c)[: min(CHUNK, NI - c * CHUNK)], normalize=True)
+        Df, If, stf, _ = full.search_device(q, K, normalize=True, nprobe=NPROBE)
+        same_ids, same_d = torch.equal(Im, If), torch.equal(Dm, Df)
+        if kind == "IVFPQ" and not same_ids:     # exact ADC ties may sit astride the k-th place: compare as sets + scores
+            same_ids = all(set(a.tolist()) == set(b.tolist()) for a, b in zip(Im[:, :K - 50], If[:, :K - 50]))
+        good = same_ids and same_d and int((st != 0).sum()) == 0 and int((stf != 0).sum()) == 0
+        ok = ok and good
+        print(f"multi_gpu_check world={world} {kind}: ids identical={same_ids} scores identical={same_d} "
+              f"status_nonzero={int((st != 0).sum())}/{int((stf != 0).sum())} -> {'PASS' if good else 'FAIL'}")
+    del shi
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
