@@ -57,13 +57,23 @@ class _DeviceIndex:
         self._torch = torch
         self._lib = _lib.load()
         self.d = int(d)
+        # The kernels tile the contraction dimension in 64-element (128-byte, swizzled) chunks.  Other
+        # dimensions are zero-padded to the next multiple of 64 on the way in (inner products, norms and
+        # centroids are unchanged by zero columns) and sliced back on the way out.
+        self._dp = (self.d + 63) // 64 * 64
+        if not (1 <= self.d <= 256):
+            raise ValueError(f"dimension {d} not supported: the B200 scan kernels hold a 128-query block of up to "
+                             "256 dimensions in shared memory")
+        if pq_m and self._dp != self.d:
+            raise ValueError("IVFPQ needs a dimension that is a multiple of 64 (sub-quantiser slices must not "
+                             "straddle padding)")
         if device is None:
             device = torch.cuda.current_device()
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
         torch.cuda.init()
         torch.zeros(1, device=self.device)  # make sure the primary context exists
         h = C.c_void_p()
-        _lib.check(self._lib.b2r_index_create(C.byref(h), self.kind, self.d, int(nlist), int(pq_m),
+        _lib.check(self._lib.b2r_index_create(C.byref(h), self.kind, self._dp, int(nlist), int(pq_m),
                                               int(pq_bits), self.metric, self.device.index))
         self._h = h
         self._ws = None
@@ -106,7 +116,7 @@ class _DeviceIndex:
             t = x.detach()
             if t.dim() != 2 or t.shape[1] != self.d:
                 raise ValueError(f"{what}: expected shape [n, {self.d}], got {tuple(t.shape)}")
-            return t.to(device=self.device, dtype=torch.float32).contiguous()
+            return self._pad(t.to(device=self.device, dtype=torch.float32).contiguous())
         a = np.asarray(x)
         if a.ndim != 2 or a.shape[1] != self.d:
             raise ValueError(f"{what}: expected shape [n, {self.d}], got {a.shape}")
@@ -115,8 +125,13 @@ class _DeviceIndex:
             import warnings
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore", UserWarning)
-                return torch.from_numpy(a).to(self.device, non_blocking=False)
-        return torch.from_numpy(a).to(self.device, non_blocking=False)
+                return self._pad(torch.from_numpy(a).to(self.device, non_blocking=False))
+        return self._pad(torch.from_numpy(a).to(self.device, non_blocking=False))
+
+    def _pad(self, t):
+        if self._dp == self.d:
+            return t
+        return self._torch.nn.functional.pad(t, (0, self._dp - self.d))
 
     def _workspace(self, nbytes: int):
         torch = self._torch
@@ -165,8 +180,13 @@ class _DeviceIndex:
     def search_device(self, q, k: int, *, normalize: bool = False, nprobe: int = 0, tau=None,
                       want_status: bool = True):
         """Asynchronous search on device tensors. Returns (D, I, status, tau_retry) CUDA tensors."""
+        return self._search_prepared(self._to_device_f32(q, "search"), k, normalize=normalize, nprobe=nprobe,
+                                     tau=tau, want_status=want_status)
+
+    def _search_prepared(self, qt, k: int, *, normalize: bool = False, nprobe: int = 0, tau=None,
+                         want_status: bool = True):
+        """`search_device` on queries that already went through `_to_device_f32` (fp32, on device, padded)."""
         torch = self._torch
-        qt = self._to_device_f32(q, "search")
         nq = qt.shape[0]
         k = int(k)
         with torch.cuda.device(self.device):
@@ -197,7 +217,7 @@ class _DeviceIndex:
         qt = self._to_device_f32(x, "search")
         if not return_device and qt.shape[0] >= 2 * _PIPE_CHUNK:
             return self._search_pipelined(qt, k, normalize, nprobe)
-        D, I, status, tau_retry = self.search_device(qt, k, normalize=normalize, nprobe=nprobe)
+        D, I, status, tau_retry = self._search_prepared(qt, k, normalize=normalize, nprobe=nprobe)
         # results + status ride to pinned host buffers in one batch of async copies, one sync
         st_h = self._to_pinned(status)
         D_h = I_h = None
@@ -232,7 +252,7 @@ class _DeviceIndex:
         keep, taus = [], []
         for lo in range(0, nq, _PIPE_CHUNK):
             hi = min(nq, lo + _PIPE_CHUNK)
-            D, I, st, tr = self.search_device(qt[lo:hi], k, normalize=normalize, nprobe=nprobe)
+            D, I, st, tr = self._search_prepared(qt[lo:hi], k, normalize=normalize, nprobe=nprobe)
             ev = torch.cuda.Event()
             ev.record(main)
             with torch.cuda.stream(side):
@@ -267,7 +287,7 @@ class _DeviceIndex:
             if prev_tau is not None and prev_tau.shape == tau_host.shape and np.array_equal(prev_tau, tau_host):
                 break  # no progress (e.g. a tie group larger than the candidate buffer)
             prev_tau = tau_host
-            D2, I2, st2, tr2 = self.search_device(qt.index_select(0, bad_t), k, normalize=normalize,
+            D2, I2, st2, tr2 = self._search_prepared(qt.index_select(0, bad_t), k, normalize=normalize,
                                                   nprobe=nprobe, tau=tau)
             if D_dev is not None:
                 D_dev.index_copy_(0, bad_t, D2)
@@ -299,18 +319,18 @@ class _DeviceIndex:
         with torch.cuda.device(self.device):
             sp = _stream_ptr(torch, self.device)
             if self.kind == _lib.KIND_FLAT:
-                out = torch.empty((n, self.d), dtype=torch.float32, device=self.device)
+                out = torch.empty((n, self._dp), dtype=torch.float32, device=self.device)
                 _lib.check(self._lib.b2r_index_get_vectors(self._h, int(i0), int(n), out.data_ptr(), sp))
-                return out
+                return out if self._dp == self.d else out[:, :self.d].contiguous()
             # IVF stores rows sorted by list: fetch everything, undo the permutation
             nt = self.ntotal
-            rows = torch.empty((nt, self.d), dtype=torch.float32, device=self.device)
+            rows = torch.empty((nt, self._dp), dtype=torch.float32, device=self.device)
             labels = torch.empty(nt, dtype=torch.int64, device=self.device)
             _lib.check(self._lib.b2r_index_get_vectors(self._h, 0, nt, rows.data_ptr(), sp))
             _lib.check(self._lib.b2r_index_get_labels(self._h, 0, nt, labels.data_ptr(), sp))
             out = torch.empty_like(rows)
             out[labels] = rows
-            return out[i0:i0 + n].contiguous()
+            return out[i0:i0 + n, :self.d].contiguous()
 
     # test-only: the full bf16 score matrix via the tcgen05 dump mode / a CUDA-core loop
     def debug_scores(self, x, impl: str = "tc", normalize: bool = False):
@@ -320,7 +340,7 @@ class _DeviceIndex:
         with torch.cuda.device(self.device):
             sp = _stream_ptr(torch, self.device)
             if impl == "tc":
-                ws = self._workspace(((qt.shape[0] + 255) // 256 * 256) * self.d * 8 + (1 << 16))
+                ws = self._workspace(((qt.shape[0] + 255) // 256 * 256) * self._dp * 8 + (1 << 16))
                 _lib.check(self._lib.b2r_debug_scores_tc(self._h, qt.shape[0], qt.data_ptr(), int(normalize),
                                                          out.data_ptr(), ws.data_ptr(), ws.numel(), sp))
             else:

@@ -34,14 +34,16 @@ class IndexIVFFlat(_DeviceIndex):
 
     # ---- parity plumbing -----------------------------------------------------------
     def export_centroids(self) -> np.ndarray:
-        out = np.empty((self.nlist, self.d), dtype=np.float32)
+        out = np.empty((self.nlist, self._dp), dtype=np.float32)
         _lib.check(self._lib.b2r_index_export_centroids(self._h, out.ctypes.data))
-        return out
+        return out if self._dp == self.d else np.ascontiguousarray(out[:, :self.d])
 
     def import_centroids(self, centroids) -> None:
         c = np.ascontiguousarray(centroids, dtype=np.float32)
         if c.shape != (self.nlist, self.d):
             raise ValueError(f"centroids must be [{self.nlist}, {self.d}]")
+        if self._dp != self.d:
+            c = np.ascontiguousarray(np.pad(c, ((0, 0), (0, self._dp - self.d))))
         with self._torch.cuda.device(self.device):
             _lib.check(self._lib.b2r_index_import_centroids(self._h, c.ctypes.data))
 

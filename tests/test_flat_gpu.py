@@ -299,3 +299,38 @@ def test_topk_merge_matches_unsharded(fr, built_lib):
                                         I_out.data_ptr(), 1, int(torch.cuda.current_stream().cuda_stream)))
     assert np.array_equal(I_out.cpu().numpy(), Iref)
     assert np.array_equal(D_out.cpu().numpy(), Dref)
+
+
+@pytest.mark.parametrize("d", [20, 32, 100, 130, 200, 255])
+def test_any_dimension_up_to_256(fr, d, tmp_path):
+    """The reference takes any `dimension` (faiss_retrieval.py:20-24); dimensions that are not a multiple
+    of 64 are zero-padded on the way in and must give the oracle's answer, the stored rows back, and a
+    faiss-layout file of the TRUE dimension."""
+    from movie_recommender_demo_b200 import faiss_io
+    from oracle.flat import normalize_L2
+    _parity(fr, 30000, 19, 100, d=d, seed=d)
+    _parity(fr, 400000, 6, 500, d=d, seed=d + 1, force_path=2)
+    rng = np.random.default_rng(d)
+    x = rng.standard_normal((500, d)).astype(np.float32)
+    g = fr.FAISSIndex(d, 'Flat')
+    g.add(x)
+    back = g.index.reconstruct_n(0, 500).cpu().numpy()
+    assert back.shape == (500, d) and np.allclose(back, normalize_L2(x.copy()), atol=1e-6)
+    path = str(tmp_path / "odd.index")
+    g.save(path)
+    desc = faiss_io.parse(open(path, "rb"))
+    assert desc["d"] == d and desc["xb"].shape == (500, d)
+    h = fr.FAISSIndex(d, 'Flat')
+    h.load(path)
+    a, da = g.search(x[:5], k=20)
+    b, db = h.search(x[:5], k=20)
+    assert np.array_equal(a, b) and np.array_equal(da, db)
+    with pytest.raises(ValueError, match="expected shape"):
+        g.search(np.zeros((2, d + 1), np.float32), k=5)
+
+
+def test_dimension_limits(fr):
+    with pytest.raises(ValueError, match="not supported"):
+        fr.FAISSIndex(257, 'Flat')
+    with pytest.raises(ValueError, match="multiple of 64"):
+        fr.FAISSIndex(100, 'IVFPQ', nlist=4)

@@ -103,3 +103,24 @@ def test_ivf_kmeans_quality_and_save_load(fr, tmp_path):
     assert h.index_type == 'IVF' and h.index.ntotal == N and h.nprobe == 8
     ids2, dist2 = h.search(q, k=100)
     assert np.array_equal(ids, ids2) and np.array_equal(dist, dist2)
+
+
+def test_ivf_odd_dimension(fr):
+    """IVF-Flat with a dimension that is not a multiple of 64 (zero-padded internally): centroids come
+    back at the true dimension and the answer matches the oracle on shared centroids."""
+    from oracle.compare import compare_topk
+    from oracle.flat import OracleFAISSIndex
+    d, N, nlist = 100, 30000, 32
+    x = _clustered(N, d, 64, seed=21)
+    q = _clustered(23, d, 64, seed=22)
+    g = fr.FAISSIndex(d, 'IVF', nlist=nlist, nprobe=6)
+    g.add(x)
+    cent = g.index.export_centroids()
+    assert cent.shape == (nlist, d)
+    o = OracleFAISSIndex(d, 'IVF', nlist=nlist, nprobe=6)
+    o.index.set_centroids(cent)
+    o.add(x)
+    assert np.array_equal(g.index.list_sizes(), o.index.list_sizes())
+    ids, dist = g.search(q, k=200)
+    rid, rd = o.search(q, k=200, extra=32)
+    compare_topk(ids, dist, rid, rd, 200, gap_tol=1e-6)
