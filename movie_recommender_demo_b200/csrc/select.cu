@@ -53,30 +53,35 @@ __device__ void bitonic_desc(uint64_t* s, int n) {
   }
 }
 
-// Same sort for n == blockDim.x (one key per thread, kept in a register): compare-exchange
-// distances below 32 go through warp shuffles, only distances >= 32 touch shared memory.
+// Same sort with one key per thread kept in a register, n <= blockDim.x (a power of two): compare-
+// exchange distances below 32 go through warp shuffles, only distances >= 32 touch shared memory.
+// Only the first max(n, 32) threads take part (named barrier 1); the caller's next __syncthreads()
+// joins everybody again.
 __device__ void bitonic_desc_reg(uint64_t* s, int n) {
   const int i = threadIdx.x;
-  uint64_t v = s[i];
-  for (int k = 2; k <= n; k <<= 1) {
-    const bool up = (i & k) == 0;
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      uint64_t o;
-      if (j >= 32) {
-        s[i] = v;
-        __syncthreads();
-        o = s[i ^ j];
-        __syncthreads();
-      } else {
-        o = __shfl_xor_sync(0xffffffffu, v, j);
+  const int nthr = n < 32 ? 32 : n;
+  if (i < nthr) {
+    uint64_t v = i < n ? s[i] : 0ull;
+    for (int k = 2; k <= n; k <<= 1) {
+      const bool up = (i & k) == 0;
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        uint64_t o;
+        if (j >= 32) {
+          s[i] = v;
+          asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+          o = s[i ^ j];
+          asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+        } else {
+          o = __shfl_xor_sync(0xffffffffu, v, j);
+        }
+        const bool lower = (i & j) == 0;           // this thread holds the lower index of the pair
+        const bool take_max = (lower == up);       // descending run: lower index keeps the larger key
+        const uint64_t mx = v > o ? v : o, mn = v > o ? o : v;
+        v = take_max ? mx : mn;
       }
-      const bool lower = (i & j) == 0;           // this thread holds the lower index of the pair
-      const bool take_max = (lower == up);       // descending run: lower index keeps the larger key
-      const uint64_t mx = v > o ? v : o, mn = v > o ? o : v;
-      v = take_max ? mx : mn;
     }
+    if (i < n) s[i] = v;
   }
-  s[i] = v;
   __syncthreads();
 }
 
@@ -113,6 +118,29 @@ __device__ __forceinline__ void radix_pick_bin(const int* hist, int* s_rem, uint
     *s_rem = rem - cum;
     *s_prefix = prefix | ((uint32_t)(255 - (lane * 8 + b)) << shift);
   }
+}
+
+// Block-wide: high word (order-preserving score bits) of the m-th largest of keys[0, c), 1 <= m <= c.
+// MSB-first radix select, 4 passes of 8 bits over a 256-bin shared histogram.  All threads call it.
+__device__ uint32_t radix_kth_hi(const uint64_t* keys, int c, int m, int* hist, int* s_rem, uint32_t* s_prefix) {
+  const int tid = threadIdx.x;
+  uint32_t prefix = 0, mask = 0;
+  if (tid == 0) *s_rem = m;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < c; i += blockDim.x) {
+      const uint32_t key = (uint32_t)(keys[i] >> 32);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (tid < 32) radix_pick_bin(hist, s_rem, s_prefix, prefix, shift);
+    __syncthreads();
+    prefix = *s_prefix;
+    mask |= 255u << shift;
+  }
+  return prefix;
 }
 
 // ------------------------------------------------------------- kth_value ---
@@ -242,7 +270,8 @@ select_rescore_kernel(const SelectParams p) {
   __shared__ uint32_t s_prefix;
   __shared__ int s_rem;
   __shared__ int s_R;
-  __shared__ int s_c, s_over;
+  __shared__ int s_c, s_over, s_status;
+  __shared__ float s_lim;
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
   if (tid == 0) { s_c = 0; s_over = 0; }
@@ -307,27 +336,13 @@ select_rescore_kernel(const SelectParams p) {
   // ---- k-th largest candidate score (rank m = min(kk, c)), radix select on the high word
   const int m = c < kk ? c : kk;
   float kth = -INFINITY;
-  if (m >= 1) {
-    uint32_t prefix = 0, mask = 0;
-    if (tid == 0) s_rem = m;
-    for (int pass = 0; pass < 4; ++pass) {
-      const int shift = 24 - 8 * pass;
-      if (tid < 256) hist[tid] = 0;
-      __syncthreads();
-      for (int i = tid; i < c; i += blockDim.x) {
-        const uint32_t key = (uint32_t)(keys[i] >> 32);
-        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
-      }
-      __syncthreads();
-      if (tid < 32) radix_pick_bin(hist, &s_rem, &s_prefix, prefix, shift);
-      __syncthreads();
-      prefix = s_prefix;
-      mask |= 255u << shift;
-    }
-    kth = ord2f(prefix);
-  }
+  if (m >= 1) kth = ord2f(radix_kth_hi(keys, c, m, hist, &s_rem, &s_prefix));
   const float lim = p.rescore ? kth - margin : kth;
   if (p.rescore && c >= kk && kk > 0 && tau_q > lim) status |= B2R_ST_NEED_LOWER_TAU;
+  if (tid == 0) {   // parked in shared memory: the register budget is 32 and these are needed only at the very end
+    s_status = status;
+    s_lim = lim;
+  }
 
   // ---- compact the rescore window into rkeys (unordered)
   if (tid == 0) s_R = 0;
@@ -345,6 +360,7 @@ select_rescore_kernel(const SelectParams p) {
     // window larger than the buffer: keep the best kRescoreMax by scan score.  With a rescore that is
     // not provably exact; without one (keys already final) the best kRescoreMax >= k are the answer.
     if (p.rescore) status |= B2R_ST_RESCORE_OVERFLOW;
+    if (tid == 0) s_status = status;
     __syncthreads();
     const int P = next_pow2(c > 1 ? c : 1);
     for (int i = c + tid; i < P; i += blockDim.x) keys[i] = 0;
@@ -356,54 +372,90 @@ select_rescore_kernel(const SelectParams p) {
   }
 
   if (p.rescore) {
-    // exact fp32 dot against the master rows: one warp per row, 4 rows in flight per warp
+    // exact fp32 dot against the master rows: 8 lanes per row (each LDG.128 of a row group reads 128
+    // contiguous bytes), 4 rows per warp pass, 4 loads in flight per lane; one accumulator per lane
+    // and a 3-step shuffle reduction.  Sized for the 32-register budget of 2 x 1024 threads per SM.
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const int sub = lane >> 3, l8 = lane & 7;
     const int nv = p.d >> 2;
+    const uint32_t row_bytes = (uint32_t)p.d * 4u;
+    const char* xbase = reinterpret_cast<const char*>(p.x32);
+    const float4* qv4 = reinterpret_cast<const float4*>(qv);
+    const bool full = (nv & 31) == 0;   // d = 128 or 256: every pass is complete, no bounds predicates
     for (int i0 = warp * 4; i0 < R; i0 += nwarps * 4) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      uint32_t idx[4];
+      const int i = i0 + sub;
+      const uint32_t ix = key_idx(rkeys[i < R ? i : R - 1]);   // past the window: re-read its last row
+      const float4* xp = reinterpret_cast<const float4*>(xbase + (uint64_t)ix * row_bytes) + l8;
+      const float4* qp = qv4 + l8;
+      float acc = 0.f;
+      if (full) {
+#pragma unroll 1
+        for (int t = 0; t < nv; t += 32) {
+          float4 xv[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) idx[u] = (i0 + u < R) ? key_idx(rkeys[i0 + u]) : 0u;
-      for (int j = lane; j < nv; j += 32) {
-        const float4 qq = reinterpret_cast<const float4*>(qv)[j];
-        float4 xv[4];
+          for (int u = 0; u < 4; ++u) xv[u] = __ldg(xp + t + u * 8);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          xv[u] = (i0 + u < R) ? __ldg(reinterpret_cast<const float4*>(p.x32 + (size_t)idx[u] * p.d) + j)
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          acc[u] = fmaf(xv[u].x, qq.x, acc[u]);
-          acc[u] = fmaf(xv[u].y, qq.y, acc[u]);
-          acc[u] = fmaf(xv[u].z, qq.z, acc[u]);
-          acc[u] = fmaf(xv[u].w, qq.w, acc[u]);
+          for (int u = 0; u < 4; ++u) {
+            const float4 qq = qp[t + u * 8];
+            acc = fmaf(xv[u].x, qq.x, acc);
+            acc = fmaf(xv[u].y, qq.y, acc);
+            acc = fmaf(xv[u].z, qq.z, acc);
+            acc = fmaf(xv[u].w, qq.w, acc);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int t = l8; t < nv; t += 8) {
+          const float4 xv = __ldg(xp + t - l8), qq = qv4[t];
+          acc = fmaf(xv.x, qq.x, acc);
+          acc = fmaf(xv.y, qq.y, acc);
+          acc = fmaf(xv.z, qq.z, acc);
+          acc = fmaf(xv.w, qq.w, acc);
         }
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
-      }
-      __syncwarp();
-      if (lane < 4 && i0 + lane < R) {
-        const float a = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
-        const uint32_t ix = lane == 0 ? idx[0] : lane == 1 ? idx[1] : lane == 2 ? idx[2] : idx[3];
-        rkeys[i0 + lane] = make_key(a, p.perm ? p.perm[ix] : ix);   // final order is by label
-      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (l8 == 0 && i < R) rkeys[i] = make_key(acc, p.perm ? p.perm[ix] : ix);   // final order is by label
     }
   }
-  const int R2 = next_pow2(R > 1 ? R : 1);
-  for (int i = R + tid; i < R2; i += blockDim.x) rkeys[i] = 0;
   __syncthreads();
-  if (R2 == (int)blockDim.x) bitonic_desc_reg(rkeys, R2);
-  else bitonic_desc(rkeys, R2);
 
-  const int avail = R < kk ? R : kk;
+  // ---- final order.  When the window is larger than it has to be for the sort size (typical:
+  // k = 500, window ~560 -> a 1024-key sort), first cut it down to the exact top-kk (plus score ties)
+  // with a radix select on the exact scores, so that the bitonic sort runs on next_pow2(kk) keys.
+  uint64_t* sbuf = rkeys;
+  int n_sort = R;
+  const int P_need = next_pow2(kk > 1 ? kk : 1);
+  if (kk >= 1 && R > kk && P_need < next_pow2(R)) {
+    const uint32_t kth_hi = radix_kth_hi(rkeys, R, kk, hist, &s_rem, &s_prefix);
+    if (tid == 0) s_R = 0;
+    __syncthreads();
+    for (int i = tid; i < R; i += blockDim.x) {
+      const uint64_t key = rkeys[i];
+      if ((uint32_t)(key >> 32) >= kth_hi) {
+        const int pos = atomicAdd(&s_R, 1);
+        if (pos < P_need) keys[pos] = key;
+      }
+    }
+    __syncthreads();
+    if (s_R <= P_need) {   // else: more ties at the k-th score than the smaller sort holds
+      sbuf = keys;
+      n_sort = s_R;
+    }
+  }
+  const int R2 = next_pow2(n_sort > 1 ? n_sort : 1);
+  for (int i = n_sort + tid; i < R2; i += blockDim.x) sbuf[i] = 0;
+  __syncthreads();
+  if (R2 <= (int)blockDim.x) bitonic_desc_reg(sbuf, R2);
+  else bitonic_desc(sbuf, R2);
+
+  const int avail = n_sort < kk ? n_sort : kk;
   for (int j = tid; j < p.k; j += blockDim.x) {
     float dv;
     int64_t iv;
     if (j < avail) {
-      const uint64_t key = rkeys[j];
+      const uint64_t key = sbuf[j];
       const uint32_t idx = key_idx(key);
       dv = p.negate_out ? -key_score(key) : key_score(key);
       iv = p.ids ? p.ids[idx] : (p.label_base + (int64_t)idx);
@@ -415,11 +467,12 @@ select_rescore_kernel(const SelectParams p) {
     p.I[(size_t)q * p.k + j] = iv;
   }
   if (tid == 0) {
-    if (p.status) p.status[q] = status;
+    const int status_f = s_status;
+    if (p.status) p.status[q] = status_f;
     if (p.tau_retry) {
-      float tr = lim;
-      if (status & B2R_ST_TOO_FEW) tr = -INFINITY;
-      else if (status & B2R_ST_CAND_OVERFLOW) tr = fmaxf(lim, tau_q);
+      float tr = s_lim;
+      if (status_f & B2R_ST_TOO_FEW) tr = -INFINITY;
+      else if (status_f & B2R_ST_CAND_OVERFLOW) tr = fmaxf(tr, p.tau[q]);
       p.tau_retry[q] = tr;
     }
   }
