@@ -102,7 +102,9 @@ int b2r_index_set_label_base(b2r_index* h, int64_t base);
  * an 8x smaller rounding error hence a smaller rescore window); rescore_eps = relative scan
  * score error bound for the rescore window (default 2^-8*1.02 bf16 / 2^-10*1.02 fp16 =
  * rigorous); cand_factor = target candidates per query as a multiple of k (default 4 bf16 /
- * 2.5 fp16); rescore = 0 returns scan scores of the unit-norm query instead of exact fp32. */
+ * 2.5 fp16); rescore = 0 returns scan scores of the unit-norm query instead of exact fp32;
+ * ivf_sample = 1 (default) lets IVF searches estimate the candidate threshold from a score sample
+ * with an exact fallback, 0 always runs the exact radix passes (same answers, more sweeps). */
 int b2r_index_set_param(b2r_index* h, const char* name, double value);
 double b2r_index_get_param(const b2r_index* h, const char* name);
 

@@ -160,6 +160,8 @@ struct b2r_index {
   int cand_cap = 4096;
   int rescore = 1;
   int force_path = 0;  // 0 auto, 1 dense, 2 filter (tests)
+  int ivf_debug = 0;   // profiling experiments (never set in production)
+  int ivf_sample = 1;  // IVF candidate threshold from a score sample (0: always the exact radix passes)
   int64_t dense_budget = (int64_t)1 << 30;  // bytes of dumped scores per query chunk
   // optional CUDA-event timing of the dominant (filter scan) kernel, for bench.py's roofline
   int profile = 0;

@@ -258,10 +258,13 @@ __global__ void build_units_kernel(const int64_t* __restrict__ list_off, const i
 // Same TMA -> tcgen05 -> TMEM pipeline as scan_tc_kernel<1, DUMP>, but work units come from a
 // device-built descriptor array (one unit = 128 gathered queries x <= 8 tiles of one list).
 constexpr int kIvfThreads = 384;
-constexpr int kIvfNS = 9, kIvfNB = 4;
+constexpr int kIvfNS = 7, kIvfNB = 4;
 constexpr int kIvfABytes = 4 * 16384, kIvfBBytes = kIvfNS * 16384;
 constexpr int kIvfNBars = 2 * kIvfNS + 2 * kIvfNB + 2;
-constexpr int kIvfSmem = 1024 + kIvfABytes + kIvfBBytes + kIvfNBars * 8 + 64;
+// per epilogue warp: a 32 x 32 fp32 transpose buffer, rows padded to 36 floats (conflict-free 128-bit
+// accesses both ways), so that the score stores leave the SM as full 128-byte row segments
+constexpr int kIvfStageRow = 36, kIvfStageBytes = 32 * kIvfStageRow * 4;
+constexpr int kIvfSmem = 1024 + kIvfABytes + kIvfBBytes + kIvfNBars * 8 + 64 + 8 * kIvfStageBytes;
 
 struct IvfScanParams {
   const IvfUnit* units;
@@ -272,6 +275,7 @@ struct IvfScanParams {
   const int* pair_sorted;     // gathered row -> pair id
   const int64_t* pair_out;    // pair id -> offset of its score run in scorebuf
   float* scorebuf;
+  int debug;                  // profiling experiments only (set_param ivf_debug): 1 = skip the score stores
 };
 
 __global__ void __launch_bounds__(kIvfThreads, 1)
@@ -290,6 +294,7 @@ ivf_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t bar_qfull = bar0 + 8u * (2 * NS + 2 * NB);
   const uint32_t bar_qempty = bar_qfull + 8u;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kIvfABytes + kIvfBBytes + kIvfNBars * 8);
+  float* stage_all = reinterpret_cast<float*>(smem + kIvfABytes + kIvfBBytes + kIvfNBars * 8 + 64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KC = p.d / kKChunk;
   if (warp == 1 && lane == 0) {
@@ -370,16 +375,24 @@ ivf_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp >= 4) {
+    // Epilogue.  A TMEM lane is a query, so a thread holds 32 consecutive scores of ITS query's run, and
+    // 32 lanes hold 32 different runs: storing straight from registers sends 32 partial lines per
+    // instruction (measured: 60 % of the kernel's time).  Each warp therefore transposes its 32 x 32
+    // block through shared memory and stores it as 128-byte row segments, 8 lanes per query.
     const int e = warp - 4, quarter = e & 3, g = e >> 2;
     const int col_begin = g * 64;
+    const int sub = lane >> 3, l8 = lane & 7;
+    float* stage = stage_all + (size_t)e * (kIvfStageBytes / 4);
+    constexpr uint32_t kNoRun = 0xFFFFFFFFu;
     int tb = 0;
     uint32_t tph = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const IvfUnit un = p.units[u];
       const int ql = quarter * 32 + lane;
       const bool warp_active = quarter * 32 < un.nq;
-      float* outp = nullptr;
-      if (ql < un.nq) outp = p.scorebuf + p.pair_out[p.pair_sorted[un.qrow0 + ql]];
+      // offset (in floats, < 2^32: the score buffer is capped at 6 GB) of this lane's query run
+      uint32_t my_run = kNoRun;
+      if (ql < un.nq) my_run = (uint32_t)p.pair_out[p.pair_sorted[un.qrow0 + ql]];
       for (int t = 0; t < un.ntiles; ++t) {
         mbar_wait(bar_tfull(tb), tph, 26);
         tc_fence_after_sync();
@@ -398,19 +411,31 @@ ivf_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int row0 = un.xrow0 + t * kTileRows + col_begin + c * 32;
             const int nvalid = un.xend - row0;                                   // real rows in this chunk
             const int npad = ((un.xend - un.xlist0 + 3) & ~3) - (row0 - un.xlist0);  // incl. the run's -inf padding
-            if (outp && npad > 0) {
-              float4* dst = reinterpret_cast<float4*>(outp + (row0 - un.xlist0));    // 16-byte aligned by construction
+            if (npad > 0 && p.debug != 1) {
+              float4* srow = reinterpret_cast<float4*>(stage + lane * kIvfStageRow);
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                if (i < npad) {
-                  float4 v;
-                  v.x = (i < nvalid) ? __uint_as_float(r[i]) : -INFINITY;
-                  v.y = (i + 1 < nvalid) ? __uint_as_float(r[i + 1]) : -INFINITY;
-                  v.z = (i + 2 < nvalid) ? __uint_as_float(r[i + 2]) : -INFINITY;
-                  v.w = (i + 3 < nvalid) ? __uint_as_float(r[i + 3]) : -INFINITY;
-                  dst[i >> 2] = v;
+              for (int i = 0; i < 32; i += 4)
+                srow[i >> 2] = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
+                                           __uint_as_float(r[i + 3]));
+              __syncwarp();
+              const int col = 4 * l8;
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int qi = it * 4 + sub;
+                const uint32_t run = __shfl_sync(0xffffffffu, my_run, qi);
+                if (run != kNoRun && col < npad) {
+                  float4 v = *reinterpret_cast<const float4*>(stage + qi * kIvfStageRow + col);
+                  if (col + 3 >= nvalid) {
+                    if (col >= nvalid) v.x = -INFINITY;
+                    if (col + 1 >= nvalid) v.y = -INFINITY;
+                    if (col + 2 >= nvalid) v.z = -INFINITY;
+                    v.w = -INFINITY;
+                  }
+                  // 16-byte aligned by construction (runs start on multiples of 4 floats)
+                  *reinterpret_cast<float4*>(p.scorebuf + (size_t)run + (size_t)(row0 - un.xlist0) + col) = v;
                 }
               }
+              __syncwarp();
             }
           }
         } else {
@@ -438,7 +463,8 @@ __global__ void __launch_bounds__(kIvfSelThreads)
 ivf_threshold_kernel(const float* __restrict__ scorebuf, int64_t smax, const int* __restrict__ row_len, int m,
                      const int64_t* __restrict__ coarse, int nprobe, const int64_t* __restrict__ list_off,
                      float* __restrict__ tau, int* __restrict__ cand_count, uint2* __restrict__ cand, int cap,
-                     const float* __restrict__ qnorm, const float* __restrict__ maxnorm, float eps, int npass) {
+                     const float* __restrict__ qnorm, const float* __restrict__ maxnorm, float eps, int npass,
+                     int sample_stride, int c_target) {
   __shared__ int hist[256];
   __shared__ uint32_t s_prefix;
   __shared__ int s_rem, s_count;
@@ -468,24 +494,24 @@ ivf_threshold_kernel(const float* __restrict__ scorebuf, int64_t smax, const int
     s_count = 0;
   }
   __syncthreads();
-  float t;
-  if (m >= T) {
-    t = -INFINITY;
-  } else {
-    // MSB-first radix select, `npass` bytes of the order-preserving key.  Stopping early leaves the low
-    // key bits zero = a LOWER bound of the k-th score (<= 2^-7 / 2^-15 relative below it): still a valid
-    // threshold (a few more candidates), one or two sweeps less over the run.
+  const float4* row4 = reinterpret_cast<const float4*>(row);
+  const int T4 = T >> 2;
+
+  // MSB-first radix select of the `rank`-th largest among the float4 vectors {row4[i * stride]}, over
+  // `passes` bytes of the order-preserving key.  Stopping early leaves the low key bits zero = a LOWER
+  // bound of that score (<= 2^-7 / 2^-15 relative below it): still a valid threshold (a few more
+  // candidates), one or two sweeps less.  128-bit loads (runs are 16-byte aligned and padded to a multiple
+  // of 4), two vectors in flight per thread; run-length aggregation: a query's scores share their leading
+  // key bytes, so a thread's consecutive elements mostly hit the same bin -> one shared atomic per run.
+  auto radix_rank = [&](int stride, int rank, int passes) -> float {
+    const int n4 = T4 / stride;
     uint32_t prefix = 0, mask = 0;
-    for (int pass = 0; pass < npass; ++pass) {
+    if (threadIdx.x == 0) s_rem = rank;
+    for (int pass = 0; pass < passes; ++pass) {
       const int shift = 24 - 8 * pass;
       for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
       __syncthreads();
       {
-        // 128-bit loads (runs are 16-byte aligned and padded to a multiple of 4), two vectors in flight
-        // per thread; run-length aggregation: a query's scores share their leading key bytes, so a
-        // thread's consecutive elements mostly hit the same bin -> one shared atomic per run
-        const float4* row4 = reinterpret_cast<const float4*>(row);
-        const int T4 = T >> 2;
         int last = -1, run = 0;
         auto feed = [&](float f) {
           const uint32_t key = f2ord(f);
@@ -500,12 +526,12 @@ ivf_threshold_kernel(const float* __restrict__ scorebuf, int64_t smax, const int
             }
           }
         };
-        for (int i = threadIdx.x; i < T4; i += 2 * blockDim.x) {
-          const float4 a = row4[i];
+        for (int i = threadIdx.x; i < n4; i += 2 * blockDim.x) {
+          const float4 a = row4[(size_t)i * stride];
           const int i2 = i + blockDim.x;
           float4 b = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-          const bool has_b = i2 < T4;
-          if (has_b) b = row4[i2];
+          const bool has_b = i2 < n4;
+          if (has_b) b = row4[(size_t)i2 * stride];
           feed(a.x); feed(a.y); feed(a.z); feed(a.w);
           if (has_b) { feed(b.x); feed(b.y); feed(b.z); feed(b.w); }
         }
@@ -540,13 +566,13 @@ ivf_threshold_kernel(const float* __restrict__ scorebuf, int64_t smax, const int
       prefix = s_prefix;
       mask |= 255u << shift;
     }
-    t = ord2f(prefix);
-    if (qnorm) t -= rescore_margin(eps, qnorm[q], *maxnorm);   // candidates = the provable rescore window
-  }
-  if (threadIdx.x == 0) tau[q] = t;
-  {
-    const float4* row4 = reinterpret_cast<const float4*>(row);
-    const int T4 = T >> 2;
+    return ord2f(prefix);
+  };
+
+  // one sweep: compact the scores >= t into this query's candidate list; returns how many there were
+  auto emit_all = [&](float t) -> int {
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
     auto emit = [&](float v, int i) {
       if (v >= t && v > -INFINITY) {
         const int slot = atomicAdd(&s_count, 1);
@@ -562,7 +588,34 @@ ivf_threshold_kernel(const float* __restrict__ scorebuf, int64_t smax, const int
       const float4 a = row4[i];
       emit(a.x, 4 * i); emit(a.y, 4 * i + 1); emit(a.z, 4 * i + 2); emit(a.w, 4 * i + 3);
     }
+    __syncthreads();
+    return s_count;
+  };
+
+  // Sampled threshold: the rank-(c_target / stride) score of every stride-th vector estimates the score of
+  // rank c_target (2.5 k) of the whole run; one sweep then collects ~c_target candidates, a superset of
+  // the top-k and of its rescore window with a margin of several sigma.  If the count comes out short
+  // (or over the buffer) this query falls back to the exact radix passes below -- so a sampled threshold
+  // never changes the answer, it only saves sweeps.
+  float t = -INFINITY;
+  bool done = false;
+  if (m >= T) {
+    emit_all(t);
+    done = true;
+  } else if (sample_stride >= 2) {
+    const int rank_s = (c_target + sample_stride - 1) / sample_stride;
+    if ((int64_t)(T4 / sample_stride) * 4 >= (int64_t)rank_s * 8) {
+      t = radix_rank(sample_stride, rank_s, 4);
+      const int got = emit_all(t);
+      done = got >= m + (c_target - m) / 4 && got <= cap;
+    }
   }
+  if (!done) {
+    t = radix_rank(1, m, npass);
+    if (qnorm) t -= rescore_margin(eps, qnorm[q], *maxnorm);   // candidates = the provable rescore window
+    emit_all(t);
+  }
+  if (threadIdx.x == 0) tau[q] = t;
   __syncthreads();
   if (threadIdx.x == 0) cand_count[q] = s_count;
 }
@@ -865,7 +918,7 @@ int ivf_add_codes(b2r_index* h, int64_t n, const uint8_t* codes, const int64_t* 
 // ---- search -------------------------------------------------------------------------
 namespace {
 struct IvfPlan {
-  int nprobe = 1, chunk = 0, qpad = 0, max_units = 0, cap = 4096, c_target = 0;
+  int nprobe = 1, chunk = 0, qpad = 0, max_units = 0, cap = 4096, c_target = 0, sample_stride = 1;
   int64_t smax = 0, pairs_pad = 0;
   size_t off_q16, off_q32, off_qnorm, off_coarse, off_cdist, off_pair_out, off_row_len, off_listcnt, off_pairoff,
       off_cursor, off_pair_sorted, off_gq16, off_units, off_nunits, off_tau, off_count, off_cand, off_score,
@@ -889,6 +942,10 @@ IvfPlan make_ivf_plan(const b2r_index* h, int q, int k, int nprobe) {
   if (ct > 2560) ct = 2560;
   if (ct < k) ct = k;
   pl.c_target = ct;
+  // sampled threshold (ivf_threshold_kernel): every stride-th score vector, sample rank >= 64
+  pl.sample_stride = 1;
+  while (pl.sample_stride < 16 && ct / (pl.sample_stride * 2) >= 64) pl.sample_stride *= 2;
+  if (h->ivf_sample == 0) pl.sample_stride = 1;
   const int64_t budget = (int64_t)6 << 30;   // score runs of one query chunk (fewer chunks = fewer passes over the lists)
   int64_t qc = budget / (pl.smax * 4);
   if (qc < 1) qc = 1;
@@ -1017,13 +1074,15 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     sp.pair_sorted = pair_sorted;
     sp.pair_out = pair_out;
     sp.scorebuf = scorebuf;
+    sp.debug = h->ivf_debug;
     ivf_scan_kernel<<<h->num_sms, kIvfThreads, kIvfSmem, stream>>>(tmQ, h->tmX, sp);
     B2R_CHECK_LAUNCH("ivf_scan_kernel");
     }
     ivf_threshold_kernel<<<qc, kIvfSelThreads, (size_t)np * 24, stream>>>(
         scorebuf, pl.smax, row_len, k, coarse, np, h->list_off, tau, count, cand, pl.cap,
         (h->rescore && !is_pq) ? qnorm : nullptr, h->maxnorm, (float)(h->scan_fp16 == 1 ? h->eps_fp16 : h->eps),
-        is_pq ? 4 : 3);   // IVF-Flat re-scores the window, a 2^-15-relative lower bound suffices; PQ needs the exact k-th
+        is_pq ? 4 : 3,    // IVF-Flat re-scores the window, a 2^-15-relative lower bound suffices; PQ needs the exact k-th
+        pl.sample_stride, pl.c_target);
     B2R_CHECK_LAUNCH("ivf_threshold_kernel");
     SelectParams sel;
     memset(&sel, 0, sizeof(sel));

@@ -306,17 +306,23 @@ select_rescore_kernel(const SelectParams p) {
       if (tid == 0) s_c = carry;
     }
     __syncthreads();
-    const int lane = tid & 31;
     // without a rescore (IVF-PQ) the scan score is final: key on the LABEL right away, so that the
     // selection below is canonical (score desc, label asc) even among exact ties
     const uint32_t* to_label = p.rescore ? nullptr : p.perm;
-    for (int sgi = tid >> 5; sgi < p.nseg; sgi += (blockDim.x >> 5)) {
-      const int pos0 = soff[sgi], n = soff[sgi + 1] - pos0;
-      const uint2* seg = p.cand + ((size_t)q * p.nseg + sgi) * p.cap_seg;
-      for (int i = lane; i < n; i += 32) {
-        if (pos0 + i < kKeyCap) {
-          const uint2 e = seg[i];
-          keys[pos0 + i] = make_key(__uint_as_float(e.x), to_label ? to_label[e.y] : e.y);
+    // a group of G threads copies one segment: a warp when there are many segments (flat scan: one per
+    // corpus split), the whole block when there is one (IVF: a single candidate list per query)
+    const int nwarps = blockDim.x >> 5;
+    const int G = p.nseg >= nwarps ? 32 : ((int)blockDim.x / p.nseg) & ~31;
+    const int groups = (int)blockDim.x / G, gid = tid / G, lig = tid % G;
+    if (gid < groups) {
+      for (int sgi = gid; sgi < p.nseg; sgi += groups) {
+        const int pos0 = soff[sgi], n = soff[sgi + 1] - pos0;
+        const uint2* seg = p.cand + ((size_t)q * p.nseg + sgi) * p.cap_seg;
+        for (int i = lig; i < n; i += G) {
+          if (pos0 + i < kKeyCap) {
+            const uint2 e = seg[i];
+            keys[pos0 + i] = make_key(__uint_as_float(e.x), to_label ? to_label[e.y] : e.y);
+          }
         }
       }
     }

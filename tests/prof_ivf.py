@@ -11,6 +11,8 @@ Q = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 2_000_000
 nlist = int(sys.argv[4]) if len(sys.argv) > 4 else 1024
 steps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+sample = int(sys.argv[6]) if len(sys.argv) > 6 else 1
+debug = int(sys.argv[7]) if len(sys.argv) > 7 else 0
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev).manual_seed(3)
 centres = torch.randn((nlist, 256), generator=g, device=dev)
@@ -22,6 +24,9 @@ x = torch.nn.functional.normalize(x, dim=1)
 idx = FAISSIndex(256, kind, nlist=nlist, nprobe=32, pq_m=32)
 idx.index.nprobe = 32
 idx.add(x)
+idx.index.set_param('ivf_sample', sample)
+idx.index.set_param('ivf_debug', debug)
+idx.index.set_param('profile', 0)
 q = torch.nn.functional.normalize(centres[torch.randint(0, nlist, (Q,), generator=g, device=dev)] + 0.35 * torch.randn((Q, 256), generator=g, device=dev), dim=1)
 for _ in range(2):
     idx.index.search_device(q, 500, normalize=True)
@@ -30,4 +35,19 @@ t0 = time.perf_counter()
 for _ in range(steps):
     idx.index.search_device(q, 500, normalize=True)
 torch.cuda.synchronize()
-print(f"{kind} N={N} nlist={nlist} Q={Q}: {(time.perf_counter() - t0) / steps * 1e3:.3f} ms/step")
+print(f"debug={debug} {kind} N={N} nlist={nlist} Q={Q} sample={sample}: {(time.perf_counter() - t0) / steps * 1e3:.3f} ms/step")
+import os
+if os.environ.get("PROF_TABLE"):
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(steps):
+            idx.index.search_device(q, 500, normalize=True)
+        torch.cuda.synchronize()
+    rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:14]
+    for e in rows:
+        print(f"  {e.key[:70]:70s} n={e.count:4d} total={e.device_time_total / steps / 1e3:8.3f} ms/step")
+    evs = [e for e in prof.events() if e.device_time_total > 0 and "Memset" not in e.name and "cudaLaunch" not in e.name]
+    per = len(evs) // steps
+    print("  -- launch sequence of the last step (us):")
+    for e in evs[-per:]:
+        print(f"     {e.device_time_total:9.1f}  {e.name[:90]}")

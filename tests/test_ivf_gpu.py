@@ -124,3 +124,22 @@ def test_ivf_odd_dimension(fr):
     ids, dist = g.search(q, k=200)
     rid, rd = o.search(q, k=200, extra=32)
     compare_topk(ids, dist, rid, rd, 200, gap_tol=1e-6)
+
+
+@pytest.mark.parametrize("kind,k", [("IVF", 500), ("IVF", 100), ("IVFPQ", 500)])
+def test_sampled_threshold_never_changes_the_answer(fr, kind, k):
+    """The IVF candidate threshold estimated from a score sample (default) must return exactly what the
+    exact radix passes return: same ids, same distances, no status flags."""
+    d, N, nlist = 128, 200000, 64
+    x = _clustered(N, d, 128, seed=31)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    q = _clustered(150, d, 128, seed=32)
+    g = fr.FAISSIndex(d, kind, nlist=nlist, nprobe=16, pq_m=16)
+    g.add(x)
+    out = {}
+    for sample in (1, 0):
+        g.index.set_param("ivf_sample", sample)
+        assert g.index.get_param("ivf_sample") == sample
+        out[sample] = g.search(q, k=k)
+        assert (g.index.last_status == 0).all()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
