@@ -66,8 +66,11 @@ Plan make_plan(const b2r_index* h, int q, int k, bool have_tau) {
   if (ct > ct_max) ct = ct_max;
   if (ct < k) ct = k;
   pl.c_target = ct;
-  // dense path when the sampled group maxima cannot resolve the threshold rank
-  const bool small = N < (int64_t)256 * ct;
+  // dense path (dump all scores, exact k-th) only when the corpus is so small that the sampled group
+  // maxima cannot resolve the threshold rank: each 32-row group would hold about one candidate or more.
+  // Above that the filter path wins even at 100k rows (its threshold costs two short launches, the
+  // dense path's per-query radix sweeps over N dumped scores do not parallelise at small batch).
+  const bool small = N < (int64_t)32 * ct;
   pl.dense = !have_tau && (h->force_path == 1 || (h->force_path == 0 && small));
   if (h->force_path == 2) pl.dense = false;
   int chunk = q;
@@ -105,7 +108,12 @@ Plan make_plan(const b2r_index* h, int q, int k, bool have_tau) {
     pl.s_tiles = (int)st;
     pl.gstride = (int64_t)pl.s_tiles * (kTileRows / kGroupCols);
     const double frac = (double)pl.s_tiles * kTileRows / (double)N;
-    int m = (int)llround(ct * frac);
+    // expected candidates in the sample = ct * frac, spread over G groups of 32 rows; the sampling pass
+    // keeps one maximum per group, so the rank to read off is the expected number of DISTINCT groups hit,
+    // G (1 - exp(-ct frac / G)) -- equal to ct * frac when candidates are sparse, lower when they collide.
+    const double G = (double)pl.gstride;
+    const double hit = ct * frac;
+    int m = (int)llround(G * (1.0 - exp(-hit / G)));
     if (m < 1) m = 1;
     pl.m_rank = m;
     int mq, qg;

@@ -120,7 +120,30 @@ def test_unnormalised_faiss_level_index_switches_to_bf16_and_stays_exact(fr):
 
 @pytest.mark.parametrize("N,Q,k", [(20000, 37, 50), (3000, 5, 500), (100, 3, 500), (1, 2, 10), (4096, 8, 100)])
 def test_dense_path_matches_oracle(fr, N, Q, k):
-    _parity(fr, N, Q, k, seed=N)
+    _parity(fr, N, Q, k, seed=N, force_path=1)
+    _parity(fr, N, Q, k, seed=N + 7)            # whichever path the planner picks for this size
+
+
+@pytest.mark.parametrize("N,Q,k", [(45000, 9, 500), (60000, 130, 500), (100000, 1, 500), (8000, 4, 100),
+                                   (20000, 700, 200), (250000, 33, 1000)])
+def test_small_corpus_filter_path_thresholds_hold(fr, N, Q, k):
+    """Corpora just above the dense cut-off: candidates are dense in the sampled 32-row groups (the
+    sample rank is collision-corrected); the answer must match the oracle with no inexact flag, and the
+    planner's threshold should rarely need the retry path."""
+    from oracle.compare import compare_topk
+    from oracle.flat import OracleFAISSIndex
+    rng = np.random.default_rng(N + k)
+    x = rng.standard_normal((N, 256)).astype(np.float32)
+    q = rng.standard_normal((Q, 256)).astype(np.float32)
+    g = fr.FAISSIndex(256, 'Flat')
+    g.add(x)
+    o = OracleFAISSIndex(256, 'Flat')
+    o.add(x)
+    ids, dist = g.search(q, k=k)
+    rid, rd = o.search(q, k=k, extra=32)
+    compare_topk(ids, dist, rid, rd, k, gap_tol=GAP_TOL, score_rtol=SCORE_RTOL)
+    assert (g.index.last_status == 0).all()
+    assert g.index.last_retries <= 1
 
 
 def test_config1_shape_100k_ads_512_queries_top500(fr):
