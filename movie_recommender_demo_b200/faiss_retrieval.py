@@ -41,6 +41,24 @@ _MAX_RETRIES = 8
 _PIPE_CHUNK = 1024   # queries per chunk when device->host result copies are pipelined
 
 
+def _pipe_chunks(nq: int):
+    """Chunk boundaries for the pipelined host-result path.  Big chunks scan faster (more queries share
+    one pass over the corpus), but the LAST chunk's device->host copy cannot hide behind anything, so the
+    sizes shrink towards the tail: the last chunk is _PIPE_CHUNK queries and each earlier one at most 4x
+    its successor (a chunk's result copy takes ~1/5 of the same chunk's search, so it hides under the next)."""
+    sizes = [min(nq, _PIPE_CHUNK)]
+    left = nq - sizes[0]
+    while left > 0:
+        take = min(left, 4 * sizes[0])
+        sizes.insert(0, take)
+        left -= take
+    out, lo = [], 0
+    for s in sizes:
+        out.append((lo, lo + s))
+        lo += s
+    return out
+
+
 def _stream_ptr(torch, device) -> int:
     return int(torch.cuda.current_stream(device).cuda_stream)
 
@@ -250,8 +268,7 @@ class _DeviceIndex:
         I_h = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
         st_h = torch.empty(nq, dtype=torch.int32, pin_memory=True)
         keep, taus = [], []
-        for lo in range(0, nq, _PIPE_CHUNK):
-            hi = min(nq, lo + _PIPE_CHUNK)
+        for lo, hi in _pipe_chunks(nq):
             D, I, st, tr = self._search_prepared(qt[lo:hi], k, normalize=normalize, nprobe=nprobe)
             ev = torch.cuda.Event()
             ev.record(main)
