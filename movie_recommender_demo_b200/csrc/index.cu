@@ -507,6 +507,7 @@ int b2r_index_set_param(b2r_index* h, const char* name, double value) {
   else if (n == "dense_budget") h->dense_budget = (int64_t)value;
   else if (n == "ivf_sample") h->ivf_sample = (int)value;
   else if (n == "ivf_debug") h->ivf_debug = (int)value;
+  else if (n == "pq_scan_path") h->pq_scan_path = (int)value;
   else if (n == "profile") {
     // value > 0: (re)start timing of up to `value` filter-scan launches; 0: stop
     DeviceGuard g(h->device);

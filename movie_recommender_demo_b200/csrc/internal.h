@@ -160,6 +160,7 @@ struct b2r_index {
   int cand_cap = 4096;
   int rescore = 1;
   int force_path = 0;  // 0 auto, 1 dense, 2 filter (tests)
+  int pq_scan_path = 0;  // 0 auto (query-major when pq_m allows), 1 force the (query, list)-pair kernel (tests)
   int ivf_debug = 0;   // profiling experiments (never set in production)
   int ivf_sample = 1;  // IVF candidate threshold from a score sample (0: always the exact radix passes)
   int64_t dense_budget = (int64_t)1 << 30;  // bytes of dumped scores per query chunk
@@ -178,6 +179,8 @@ struct b2r_index {
   float* codebooks = nullptr;       // device [pq_m, 256, d/pq_m]
   uint8_t* codes = nullptr;         // device [capacity, pq_m] (sorted by list)
   float* pq_list_tab = nullptr;     // device [nlist, pq_m, 256]: 2 c_ls.y_sj + |c_ls|^2 (faiss "precomputed table")
+  float* pq_row_term = nullptr;     // device [pq_row_term_cap]: sum_s pq_list_tab[list(row)][s][code_s(row)] per stored row
+  int64_t pq_row_term_cap = 0;
   bool pq_trained = false;
 };
 
@@ -221,4 +224,5 @@ int pq_scatter_codes(const uint8_t* src, const int64_t* dst, int64_t n, int m, c
 int pq_scan(b2r_index* h, int nq, int npairs, const float* q32, const int64_t* coarse, int nprobe,
             const int64_t* pair_out, float* qtab, float* scorebuf, cudaStream_t stream);
 int pq_build_list_tables(b2r_index* h, cudaStream_t stream);
+int pq_update_row_terms(b2r_index* h, cudaStream_t stream);   // after the code storage or the quantisers changed
 }  // namespace b2r

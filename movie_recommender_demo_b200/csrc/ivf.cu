@@ -699,6 +699,7 @@ void ivf_free(b2r_index* h) {
   cudaFree(h->codebooks);
   cudaFree(h->codes);
   cudaFree(h->pq_list_tab);
+  cudaFree(h->pq_row_term);
   h->list_off = nullptr;
 }
 
@@ -778,7 +779,7 @@ static int store_codes(b2r_index* h, int64_t n, const uint8_t* codes_new, const 
     int32_t* nlistid = nullptr;
     uint32_t* nperm = nullptr;
     const int64_t cap = (int64_t)align_up((size_t)n_all, 1024);
-    if (cudaMalloc(&ncodes, (size_t)cap * m) != cudaSuccess || cudaMalloc(&nlistid, (size_t)cap * 4) != cudaSuccess ||
+    if (cudaMalloc(&ncodes, (size_t)cap * m + 64) != cudaSuccess ||   /* +64: bulk copies read 16-byte granules */ cudaMalloc(&nlistid, (size_t)cap * 4) != cudaSuccess ||
         cudaMalloc(&nperm, (size_t)cap * 4) != cudaSuccess) {
       cudaGetLastError();
       cudaFree(ncodes); cudaFree(nlistid); cudaFree(nperm);
@@ -810,7 +811,7 @@ static int store_codes(b2r_index* h, int64_t n, const uint8_t* codes_new, const 
     h->ntotal = n_all;
     h->list_sizes_host.resize(nlist);
     for (int l = 0; l < nlist; ++l) h->list_sizes_host[l] = off_host[l + 1] - off_host[l];
-    return B2R_OK;
+    return pq_update_row_terms(h, stream);
 }
 
 int ivf_add(b2r_index* h, int64_t n, const float* x, int normalize, cudaStream_t stream) {

@@ -21,6 +21,7 @@
 #include <random>
 
 #include "internal.h"
+#include "ptx.cuh"
 
 namespace b2r {
 namespace {
@@ -180,6 +181,226 @@ pq_query_tables_kernel(const float* __restrict__ q32, const float* __restrict__ 
   }
 }
 
+// t[row] = sum_s B[list(row)][s][code_s(row)]  -- the list-dependent part of the ADC distance, per stored row
+__global__ void __launch_bounds__(256)
+pq_row_terms_kernel(const uint8_t* __restrict__ codes, const int32_t* __restrict__ row_list,
+                    const float* __restrict__ B, int64_t n, int m, float* __restrict__ t) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* b = B + (size_t)row_list[i] * m * 256;
+  const uint8_t* c = codes + i * m;
+  float acc = 0.f;
+  for (int s = 0; s < m; ++s) acc += __ldg(b + s * 256 + c[s]);
+  t[i] = acc;
+}
+
+// Query-major ADC scan (pq_m in {8, 16, 32, 64}).
+//
+//   dist(q, x) = sum_s A[q][s][code_s(x)]  +  t[x]  -  2 <c_l, q>        (expansion above, regrouped)
+//                look-ups, per query          per row    per (query, list)
+//
+// so the look-up table depends on the QUERY only: one CTA builds it once and scans all the lists its
+// query probes (blockIdx.y splits the probe slots when there are few queries).  The scan is bound by
+// shared-memory look-ups; with the obvious layout lut[s][code] the 32 lanes of a warp hit random banks
+// (measured ~3.5-way conflicts, 4.4 ms at 10M x m32, Q=4096).  Here a lane owns 4 sub-quantisers (one
+// 32-bit word of the code row), M/4 lanes share a row, 128/M rows are in flight per warp pass, and the
+// table is stored as lut[code][128]: 128/M replicas of the M entries, each replica's entries rotated so
+// that in every look-up instruction the 32 lanes touch 32 distinct banks whatever the codes are.
+template <int M>
+__device__ __forceinline__ int pq_slot(int r, int j, int t) {
+  constexpr int LR = M / 4;
+  const int rho = (M <= 32) ? r / (32 / (M <= 32 ? M : 32)) : r;
+  return r * M + (((t + rho) & 3) * LR + j);
+}
+
+constexpr int kPqMaxSlots = 256;   // probe slots one CTA of the query-major scan can hold
+constexpr int kPqConsumers = 15;   // look-up warps per group; tile g belongs to group g % kPqGroups
+constexpr int kPqGroups = 2;
+constexpr int kPqThreads = (kPqGroups * kPqConsumers + 1) * 32;   // + one warp that feeds the ring
+
+template <int M> struct PqTile {
+  static constexpr int ROWS = ((M == 32) ? 1 : 2) * kPqConsumers * 32;   // code rows per tile: 1-2 blocks per warp
+  static constexpr int CODE_BYTES = ROWS * M + 16;          // <= 16 KB (+16: lists start on M-byte, not 16-byte, bounds)
+  static constexpr int TERM_BYTES = (ROWS + 4) * 4;         // the rows' list terms (+4: same for 4-byte bounds)
+  static constexpr int BYTES = CODE_BYTES + TERM_BYTES;
+  // tiles in flight (TMA bulk-copy ring): as many as fit beside the 128 KB table -- the scan is bound by
+  // bytes in flight (measured 3-4 TB/s with 3 tiles ahead)
+  static constexpr int BUFS = (M == 32) ? 5 : (M == 16) ? 4 : 7;
+};
+
+// Warp-specialised: the last warp streams (list, tile) after (list, tile) of code rows + row terms into a
+// ring of shared-memory buffers with 1-D TMA bulk copies (two instructions per tile); two groups of 15
+// consumer warps take alternate tiles: wait on the tile's mbarrier, look their 32-row blocks up, release
+// the buffer -- no block-wide barrier in the loop, so the warps drift apart and hide each other's
+// shared-memory latencies.  The loop is bound by the shared-memory pipe (look-ups + shuffles), so the M/4
+// partial sums of a warp pass are combined with a transposing butterfly: M/4 - 1 shuffles per 32 rows
+// instead of (M/4) log2(M/4).
+template <int M>
+__global__ void __launch_bounds__(kPqThreads, 1)
+ivfpq_scan_query_kernel(const float* __restrict__ q32, int d, const int64_t* __restrict__ coarse, int nprobe,
+                        const float* __restrict__ cent, const float* __restrict__ cb,
+                        const float* __restrict__ row_term, const int64_t* __restrict__ list_off,
+                        const uint8_t* __restrict__ codes, const int64_t* __restrict__ pair_out,
+                        float* __restrict__ scorebuf) {
+  using T = PqTile<M>;
+  constexpr int kPqBufs = T::BUFS;
+  constexpr int LR = M / 4, RP = 32 / LR;   // lanes per row, rows per warp pass (= replicas)
+  extern __shared__ __align__(128) uint8_t smraw[];
+  float* lut = reinterpret_cast<float*>(smraw);                       // [256][128]
+  uint8_t* tiles = smraw + 256 * 128 * 4;                             // kPqBufs x (codes | row terms)
+  float* qs = reinterpret_cast<float*>(tiles + kPqBufs * T::BYTES);   // [d]
+  int64_t* p_x0 = reinterpret_cast<int64_t*>(qs + d);                 // per probe slot of this CTA:
+  int64_t* p_out = p_x0 + kPqMaxSlots;                                //   first stored row, score-run offset,
+  int* p_len = reinterpret_cast<int*>(p_out + kPqMaxSlots);           //   list length,
+  int* p_t0 = p_len + kPqMaxSlots;                                    //   first tile number (cumulative, +1),
+  float* p_bias = reinterpret_cast<float*>(p_t0 + kPqMaxSlots + 2);   //   -2 <c_l, q>
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_bias + kPqMaxSlots); // full[kPqBufs], empty[kPqBufs]
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int dsub = d / M;
+  const int nslots = (nprobe - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;   // pr = y, y + Y, ...
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar_full = [&](int i) { return bar0 + 8u * i; };
+  auto bar_empty = [&](int i) { return bar0 + 8u * (kPqBufs + i); };
+
+  if (tid == 0) {
+    for (int i = 0; i < kPqBufs; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), kPqConsumers); }   // one group per tile
+    fence_mbar_init();
+  }
+  for (int i = tid; i < d; i += blockDim.x) qs[i] = q32[(size_t)q * d + i];
+  for (int k = tid; k < nslots; k += blockDim.x) {
+    const int pr = blockIdx.y + k * gridDim.y;
+    const int64_t l = coarse[(size_t)q * nprobe + pr];
+    int64_t x0 = 0, len = 0;
+    if (l >= 0) { x0 = list_off[l]; len = list_off[l + 1] - x0; }
+    p_x0[k] = x0;
+    p_len[k] = (int)len;
+    p_out[k] = pair_out[(size_t)q * nprobe + pr];
+  }
+  __syncthreads();
+  // look-up table: |q_s - y_sj|^2 for every (sub-quantiser s, code j), written to every replica
+  for (int i = tid; i < 256 * M; i += blockDim.x) {
+    const int c = i / M, s = i % M;
+    const float* w = cb + ((size_t)s * 256 + c) * dsub;
+    const float* qv = qs + s * dsub;
+    float acc = 0.f;
+    for (int t = 0; t < dsub; t += 4) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + t));
+      float df = qv[t] - wv.x; acc = fmaf(df, df, acc);
+      df = qv[t + 1] - wv.y; acc = fmaf(df, df, acc);
+      df = qv[t + 2] - wv.z; acc = fmaf(df, df, acc);
+      df = qv[t + 3] - wv.w; acc = fmaf(df, df, acc);
+    }
+#pragma unroll
+    for (int r = 0; r < RP; ++r) lut[c * 128 + pq_slot<M>(r, s >> 2, s & 3)] = acc;
+  }
+  // -2 <c_l, q> per probe slot: one warp per slot, the centroid's loads issued together (d <= 256)
+  for (int k = warp; k < nslots; k += nwarps) {
+    const int pr = blockIdx.y + k * gridDim.y;
+    const int64_t l = coarse[(size_t)q * nprobe + pr];
+    float cv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) cv[u] = (l >= 0 && lane + 32 * u < d) ? __ldg(cent + (size_t)l * d + lane + 32 * u) : 0.f;
+    float dot = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) dot = fmaf(cv[u], lane + 32 * u < d ? qs[lane + 32 * u] : 0.f, dot);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (lane == 0) p_bias[k] = -2.0f * dot;
+  }
+  if (tid == 0) {
+    int cum = 0;
+    for (int k = 0; k < nslots; ++k) {
+      p_t0[k] = cum;
+      cum += (p_len[k] + T::ROWS - 1) / T::ROWS;
+    }
+    p_t0[nslots] = cum;
+  }
+  __syncthreads();
+  const int ntiles = p_t0[nslots];
+  const uint32_t tiles_s = smem_u32(tiles);
+
+  if (warp == kPqGroups * kPqConsumers) {
+    // ------------------------------------------------------------------ producer
+    if (lane == 0) {
+      int k = 0;
+      for (int g = 0; g < ntiles; ++g) {
+        const int buf = g % kPqBufs, use = g / kPqBufs;
+        if (use > 0) mbar_wait(bar_empty(buf), (uint32_t)((use - 1) & 1), 41);
+        while (g >= p_t0[k + 1]) ++k;
+        const int row0 = (g - p_t0[k]) * T::ROWS;
+        const int nrows = min(T::ROWS, p_len[k] - row0);
+        const int64_t first = p_x0[k] + row0;
+        // both sources are aligned DOWN to 16 bytes; the consumers skip the same number of leading bytes
+        const uint64_t cbyte = (uint64_t)first * M;
+        const uint32_t cskip = (uint32_t)(cbyte & 15u);
+        const uint32_t cbytes = (cskip + (uint32_t)nrows * M + 15u) & ~15u;
+        const uint32_t tskip = (uint32_t)(first & 3);
+        const uint32_t tbytes = ((tskip + (uint32_t)nrows + 3u) & ~3u) * 4u;
+        const uint32_t dst = tiles_s + (uint32_t)(buf * T::BYTES);
+        mbar_arrive_expect_tx(bar_full(buf), cbytes + tbytes);
+        bulk_load_1d(dst, codes + (cbyte - cskip), cbytes, bar_full(buf));
+        bulk_load_1d(dst + T::CODE_BYTES, row_term + (first - tskip), tbytes, bar_full(buf));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ consumers
+    const int rsub = lane / LR, j = lane % LR;
+    const int grp = warp / kPqConsumers, cw = warp % kPqConsumers;
+    const float* lb[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) lb[t] = lut + pq_slot<M>(rsub, j, t);
+    int k = 0;
+#pragma unroll 1
+    for (int g = grp; g < ntiles; g += kPqGroups) {
+      const int buf = g % kPqBufs, use = g / kPqBufs;
+      while (g >= p_t0[k + 1]) ++k;
+      const int row0 = (g - p_t0[k]) * T::ROWS;
+      const int len = p_len[k];
+      const int nrows = min(T::ROWS, len - row0);
+      const int64_t first = p_x0[k] + row0;
+      const uint8_t* tile = tiles + buf * T::BYTES;
+      const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile + (((uint64_t)first * M) & 15u));
+      const float* tt = reinterpret_cast<const float*>(tile + T::CODE_BYTES) + (first & 3);
+      float* out = scorebuf + p_out[k] + row0;
+      const float b = p_bias[k];
+      mbar_wait(bar_full(buf), (uint32_t)(use & 1), 42);
+      for (int base = cw * 32; base < nrows; base += kPqConsumers * 32) {
+        float a[LR];
+#pragma unroll
+        for (int ps = 0; ps < LR; ++ps) {
+          const uint32_t w = tw[(base + ps * RP + rsub) * LR + j];   // rows past the list end: stale bytes, discarded
+          float v = lb[0][(w & 255u) * 128];
+          v += lb[1][((w >> 8) & 255u) * 128];
+          v += lb[2][((w >> 16) & 255u) * 128];
+          v += lb[3][(w >> 24) * 128];
+          a[ps] = v;
+        }
+        // transposing butterfly over the LR lanes of a row group: lane j ends with the total of pass j
+#pragma unroll
+        for (int o = LR / 2, n = LR; o >= 1; o >>= 1, n >>= 1) {
+          const bool up = (j & o) != 0;
+#pragma unroll
+          for (int i = 0; i < n / 2; ++i) {
+            const float send = up ? a[i] : a[i + n / 2];
+            const float keep = up ? a[i + n / 2] : a[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+        }
+        const int my = base + j * RP + rsub;
+        if (my < nrows) out[my] = -(a[0] + tt[my] + b);
+      }
+      if (cw == 0 && row0 + nrows == len) {
+        // last tile of the list: the run is padded to a multiple of 4 scores with -inf (16-byte aligned runs, ivf.cu)
+        const int padded = (len + 3) & ~3;
+        if (lane < padded - len) out[nrows + lane] = -INFINITY;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty(buf));
+    }
+  }
+}
+
 // One CTA per (query, probe slot) pair: LUT = A[q] + B[l] + bias in shared memory, then the list's
 // codes (128-bit loads, m shared-memory look-ups per row).  Writes NEGATED distances so that
 // "larger is better" like the inner-product paths.
@@ -333,6 +554,51 @@ int pq_build_list_tables(b2r_index* h, cudaStream_t stream) {
   }
   pq_list_tables_kernel<<<h->nlist, 256, 0, stream>>>(h->quantizer->x32, h->codebooks, h->d, h->pq_m, h->pq_list_tab);
   B2R_CHECK_LAUNCH("pq_list_tables_kernel");
+  return pq_update_row_terms(h, stream);   // stored rows (if any) depend on the tables
+}
+
+int pq_update_row_terms(b2r_index* h, cudaStream_t stream) {
+  if (h->kind != B2R_KIND_IVF_PQ || !h->pq_list_tab || !h->codes || h->ntotal <= 0) return B2R_OK;
+  if (h->pq_row_term_cap < h->ntotal) {
+    cudaFree(h->pq_row_term);
+    h->pq_row_term = nullptr;
+    const int64_t cap = (int64_t)align_up((size_t)h->ntotal, 1024);
+    if (cudaMalloc(&h->pq_row_term, (size_t)cap * 4 + 64) != cudaSuccess) {   // +64: bulk copies read 16-byte granules
+      cudaGetLastError();
+      h->pq_row_term_cap = 0;
+      return fail(B2R_ENOMEM, "cudaMalloc of the PQ per-row terms failed");
+    }
+    h->pq_row_term_cap = cap;
+  }
+  pq_row_terms_kernel<<<(unsigned)ceil_div(h->ntotal, 256), 256, 0, stream>>>(h->codes, h->row_list, h->pq_list_tab,
+                                                                             h->ntotal, h->pq_m, h->pq_row_term);
+  B2R_CHECK_LAUNCH("pq_row_terms_kernel");
+  return B2R_OK;
+}
+
+template <int M>
+static int launch_scan_query(b2r_index* h, int nq, const float* q32, const int64_t* coarse, int nprobe,
+                             const int64_t* pair_out, float* scorebuf, cudaStream_t stream) {
+  auto kern = ivfpq_scan_query_kernel<M>;
+  constexpr int kPqBufs = PqTile<M>::BUFS;
+  const size_t smem = (size_t)256 * 128 * 4 + (size_t)kPqBufs * PqTile<M>::BYTES + (size_t)h->d * 4 +
+                      (size_t)kPqMaxSlots * 28 + 16 + 2 * kPqBufs * 8;
+  static bool configured[64] = {};
+  int dev = 0;
+  B2R_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  256 * 128 * 4 + kPqBufs * PqTile<M>::BYTES + 1024 * 4 + kPqMaxSlots * 28 + 16 + 2 * kPqBufs * 8));
+    configured[dev & 63] = true;
+  }
+  // few queries: split a query's probe slots over several CTAs so that the grid still covers the SMs;
+  // many probe slots: at most kPqMaxSlots per CTA
+  int slices = (int)ceil_div(nprobe, kPqMaxSlots);
+  while (slices < nprobe && (int64_t)nq * slices < 2 * h->num_sms) ++slices;
+  dim3 grid((unsigned)nq, (unsigned)slices);
+  kern<<<grid, kPqThreads, smem, stream>>>(q32, h->d, coarse, nprobe, h->quantizer->x32, h->codebooks, h->pq_row_term,
+                                    h->list_off, h->codes, pair_out, scorebuf);
+  B2R_CHECK_LAUNCH("ivfpq_scan_query_kernel");
   return B2R_OK;
 }
 
@@ -340,6 +606,14 @@ int pq_scan(b2r_index* h, int nq, int npairs, const float* q32, const int64_t* c
             const int64_t* pair_out, float* qtab, float* scorebuf, cudaStream_t stream) {
   const int d = h->d, m = h->pq_m;
   if (!h->pq_list_tab) return fail(B2R_ESTATE, "IVF-PQ per-list tables are missing");
+  const bool query_major = (m == 8 || m == 16 || m == 32) && h->pq_row_term && (d / m) % 4 == 0 && h->pq_scan_path != 1;
+  if (query_major) {
+    switch (m) {
+      case 8: return launch_scan_query<8>(h, nq, q32, coarse, nprobe, pair_out, scorebuf, stream);
+      case 16: return launch_scan_query<16>(h, nq, q32, coarse, nprobe, pair_out, scorebuf, stream);
+      default: return launch_scan_query<32>(h, nq, q32, coarse, nprobe, pair_out, scorebuf, stream);
+    }
+  }
   pq_query_tables_kernel<<<nq, 256, (size_t)d * 4, stream>>>(q32, h->codebooks, d, m, qtab);
   B2R_CHECK_LAUNCH("pq_query_tables_kernel");
   const size_t smem = (size_t)m * 256 * 4 + (size_t)m * 4;

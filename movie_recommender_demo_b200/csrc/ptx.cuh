@@ -70,6 +70,12 @@ __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
 // 2D tiled load: coordinates (c0 = innermost element index, c1 = row index)
+// 1-D bulk copy global -> shared (TMA engine, no tensor map): 16-byte aligned src/dst, bytes % 16 == 0
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap, int c0, int c1,
                                             uint32_t bar) {
   asm volatile(

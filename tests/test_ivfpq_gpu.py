@@ -97,3 +97,24 @@ def test_ivfpq_exact_ties_are_ordered_by_label(fr):
         assert same.mean() > 0.3, "this configuration is supposed to be tie-heavy"
         assert (np.diff(I, axis=1)[same] > 0).all(), "ties must be ordered by label"
     assert np.array_equal(ids, ids2[:, :60])
+
+
+@pytest.mark.parametrize("m,Q", [(8, 5), (16, 200), (32, 64), (64, 9)])
+def test_query_major_scan_agrees_with_pair_scan(fr, m, Q):
+    """Two ADC scan kernels exist (query-major with a bank-conflict-free replicated table, and the older
+    one-CTA-per-(query, list) kernel): same codes, same tables -> distances equal to a few ulps and the
+    same result sets; both must also agree with the oracle (checked by the tests above for the default)."""
+    d, N, nlist = 256, 60000, 32
+    x = _clustered(N, d, 64, seed=41)
+    q = _clustered(Q, d, 64, seed=42)
+    g = fr.FAISSIndex(d, 'IVFPQ', nlist=nlist, nprobe=8, pq_m=m)
+    g.add(x)
+    out = {}
+    for path in (0, 1):
+        g.index.set_param("pq_scan_path", path)
+        ids, dist = g.search(q, k=100)
+        assert (g.index.last_status == 0).all()
+        out[path] = (ids, dist)
+    assert np.allclose(out[0][1], out[1][1], rtol=2e-5, atol=2e-6)
+    same = np.mean([len(set(a) & set(b)) / 100.0 for a, b in zip(out[0][0], out[1][0])])
+    assert same > 0.995
