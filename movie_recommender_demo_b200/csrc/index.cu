@@ -432,6 +432,7 @@ int b2r_index_reset(b2r_index* h) {
   h->ntotal = 0;
   B2R_CUDA(cudaMemset(h->maxnorm, 0, 256));
   std::fill(h->list_sizes_host.begin(), h->list_sizes_host.end(), 0);
+  h->list_sizes_desc_for = -1;
   if (h->list_off) B2R_CUDA(cudaMemset(h->list_off, 0, (size_t)(h->nlist + 1) * 8));
   return B2R_OK;
 }

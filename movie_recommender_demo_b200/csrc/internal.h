@@ -175,6 +175,8 @@ struct b2r_index {
   int32_t* row_list = nullptr;      // device [capacity] list id of each stored (sorted) row
   uint32_t* perm = nullptr;         // device [capacity] sorted row -> insertion label
   std::vector<int64_t> list_sizes_host;  // mirrors list sizes (workspace bounds)
+  mutable std::vector<int64_t> list_sizes_desc;  // the same, sorted descending: cached by the search planner
+  mutable int64_t list_sizes_desc_for = -1;      // ntotal the cache was built for (-1: stale)
   // ---- PQ state (kind == IVF_PQ)
   float* codebooks = nullptr;       // device [pq_m, 256, d/pq_m]
   uint8_t* codes = nullptr;         // device [capacity, pq_m] (sorted by list)
