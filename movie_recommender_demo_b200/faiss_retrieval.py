@@ -21,6 +21,7 @@ Documented deviations from the reference:
 from __future__ import annotations
 
 import ctypes as C
+import os
 import pickle
 import struct
 import time
@@ -39,6 +40,8 @@ METRIC_L2 = _lib.METRIC_L2
 _RETRY_BITS = _lib.ST_TOO_FEW | _lib.ST_NEED_LOWER_TAU | _lib.ST_CAND_OVERFLOW
 _MAX_RETRIES = 8
 _PIPE_CHUNK = 1024   # queries per chunk when device->host result copies are pipelined
+_GRAPH_MAX_Q = 256   # host-result searches up to this batch replay a captured CUDA graph (launch-bound regime)
+_GRAPH_CACHE = 16    # captured (batch, k, nprobe) shapes kept per index
 
 
 def _pipe_chunks(nq: int):
@@ -99,6 +102,7 @@ class _DeviceIndex:
         self.last_status = None  # per-query status bits of the most recent search (numpy)
         self.last_retries = 0
         self._copy_stream = None
+        self._graphs = {}        # (nq, k, normalize, nprobe) -> captured search (small batches), see _graph_entry
 
     # ------------------------------------------------------------ lifetime
     def __del__(self):
@@ -120,6 +124,7 @@ class _DeviceIndex:
         return bool(self._lib.b2r_index_is_trained(self._h))
 
     def set_param(self, name: str, value: float) -> None:
+        self._graphs = {}
         _lib.check(self._lib.b2r_index_set_param(self._h, name.encode(), float(value)))
 
     def get_param(self, name: str) -> float:
@@ -160,6 +165,7 @@ class _DeviceIndex:
 
     # ---------------------------------------------------------- faiss API
     def train(self, x) -> None:
+        self._graphs = {}
         xt = self._to_device_f32(x, "train")
         with self._torch.cuda.device(self.device):
             _lib.check(self._lib.b2r_index_train(self._h, xt.shape[0], xt.data_ptr(), 1234,
@@ -167,6 +173,7 @@ class _DeviceIndex:
 
     def add(self, x, normalize: bool = False) -> None:
         """faiss `index.add(x)`; `normalize=True` fuses faiss.normalize_L2 into the ingest."""
+        self._graphs = {}
         xt = self._to_device_f32(x, "add")
         with self._torch.cuda.device(self.device):
             _lib.check(self._lib.b2r_index_add(self._h, xt.shape[0], xt.data_ptr(), int(bool(normalize)),
@@ -174,11 +181,13 @@ class _DeviceIndex:
         self._ids_set = False
 
     def reset(self) -> None:
+        self._graphs = {}
         _lib.check(self._lib.b2r_index_reset(self._h))
         self._ids_set = False
 
     def set_ids(self, ids) -> None:
         """Device-side id map: search returns ids[label] (None clears)."""
+        self._graphs = {}
         torch = self._torch
         with torch.cuda.device(self.device):
             sp = _stream_ptr(torch, self.device)
@@ -193,6 +202,7 @@ class _DeviceIndex:
             self._ids_set = True
 
     def set_label_base(self, base: int) -> None:
+        self._graphs = {}
         _lib.check(self._lib.b2r_index_set_label_base(self._h, int(base)))
 
     def search_device(self, q, k: int, *, normalize: bool = False, nprobe: int = 0, tau=None,
@@ -232,6 +242,12 @@ class _DeviceIndex:
         the host, which rides along with the result copy."""
         torch = self._torch
         self.last_retries = 0
+        nq = len(x)
+        ent = None
+        if not return_device and 0 < nq <= _GRAPH_MAX_Q and not os.environ.get("B2R_NO_GRAPHS"):
+            ent = self._graph_entry(nq, int(k), bool(normalize), int(nprobe))
+        if ent:
+            return self._search_graph(ent, x, k, normalize, nprobe)
         qt = self._to_device_f32(x, "search")
         if not return_device and qt.shape[0] >= 2 * _PIPE_CHUNK:
             return self._search_pipelined(qt, k, normalize, nprobe)
@@ -253,6 +269,77 @@ class _DeviceIndex:
         if D_h is None:
             D_h, I_h = self._to_pinned(D), self._to_pinned(I)
             torch.cuda.current_stream(self.device).synchronize()
+        return D_h.numpy(), I_h.numpy()
+
+    # ---- small batches: the launch sequence of one search is fixed for a given (batch, k, nprobe) and a
+    #      given corpus state, and at batch <= 256 the gaps between its 6-14 short launches are a third of
+    #      the step -> capture it once in a CUDA graph (static query / result buffers), replay afterwards.
+    def _graph_entry(self, nq: int, k: int, normalize: bool, nprobe: int):
+        key = (nq, k, normalize, nprobe)
+        ent = self._graphs.get(key)
+        if ent is not None:
+            return ent
+        if self.ntotal == 0:
+            return None
+        torch = self._torch
+        with torch.cuda.device(self.device):
+            need = int(self._lib.b2r_index_search_workspace(self._h, nq, k, nprobe))
+            ent = {"q": torch.zeros((nq, self._dp), dtype=torch.float32, device=self.device),
+                   "D": torch.empty((nq, k), dtype=torch.float32, device=self.device),
+                   "I": torch.empty((nq, k), dtype=torch.int64, device=self.device),
+                   "status": torch.zeros(nq, dtype=torch.int32, device=self.device),
+                   "tau_retry": torch.empty(nq, dtype=torch.float32, device=self.device),
+                   "ws": torch.empty(max(need, 1), dtype=torch.uint8, device=self.device)}
+
+            def launch():
+                _lib.check(self._lib.b2r_index_search(
+                    self._h, nq, ent["q"].data_ptr(), int(normalize), k, nprobe, ent["D"].data_ptr(),
+                    ent["I"].data_ptr(), ent["status"].data_ptr(), ent["tau_retry"].data_ptr(), None,
+                    ent["ws"].data_ptr(), ent["ws"].numel(), _stream_ptr(torch, self.device)))
+
+            launch()    # eager once: one-time kernel attribute set-up must not happen under capture
+            torch.cuda.current_stream(self.device).synchronize()
+            graph = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(graph):
+                    launch()
+                ent["graph"] = graph
+            except Exception:      # not capturable on this build/driver: stay on the eager path for this shape
+                ent = False
+                torch.cuda.synchronize(self.device)
+        if len(self._graphs) >= _GRAPH_CACHE:
+            self._graphs.pop(next(iter(self._graphs)))
+        self._graphs[key] = ent
+        return ent
+
+    def _search_graph(self, ent, x, k, normalize, nprobe):
+        torch = self._torch
+        q = ent["q"]
+        if isinstance(x, torch.Tensor):
+            src = x.detach()
+            if src.dim() != 2 or src.shape[1] != self.d:
+                raise ValueError(f"search: expected shape [n, {self.d}], got {tuple(src.shape)}")
+        else:
+            a = np.asarray(x)
+            if a.ndim != 2 or a.shape[1] != self.d:
+                raise ValueError(f"search: expected shape [n, {self.d}], got {a.shape}")
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            if not a.flags.writeable:
+                a = a.copy()
+            src = torch.from_numpy(a)
+        with torch.cuda.device(self.device):
+            (q if self._dp == self.d else q[:, :self.d]).copy_(src, non_blocking=True)
+            ent["graph"].replay()
+            D, I = ent["D"], ent["I"]
+            st_h, D_h, I_h = self._to_pinned(ent["status"]), self._to_pinned(D), self._to_pinned(I)
+            torch.cuda.current_stream(self.device).synchronize()
+            st = st_h.numpy()
+            if (st & _RETRY_BITS).any() and self._supports_retry:
+                st = self._retry(q, k, normalize, nprobe, st.copy(), ent["tau_retry"], D, I, None, None)
+                D_h, I_h = self._to_pinned(D), self._to_pinned(I)
+                torch.cuda.current_stream(self.device).synchronize()
+        self.last_status = st
+        self._warn_status(st)
         return D_h.numpy(), I_h.numpy()
 
     def _search_pipelined(self, qt, k, normalize, nprobe):

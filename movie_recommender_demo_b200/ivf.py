@@ -39,6 +39,7 @@ class IndexIVFFlat(_DeviceIndex):
         return out if self._dp == self.d else np.ascontiguousarray(out[:, :self.d])
 
     def import_centroids(self, centroids) -> None:
+        self._graphs = {}
         c = np.ascontiguousarray(centroids, dtype=np.float32)
         if c.shape != (self.nlist, self.d):
             raise ValueError(f"centroids must be [{self.nlist}, {self.d}]")
@@ -88,6 +89,7 @@ class IndexIVFPQ(IndexIVFFlat):
         return out
 
     def import_codebooks(self, codebooks) -> None:
+        self._graphs = {}
         cb = np.ascontiguousarray(codebooks, dtype=np.float32)
         with self._torch.cuda.device(self.device):
             _lib.check(self._lib.b2r_index_import_codebooks(self._h, cb.ctypes.data))
@@ -110,6 +112,7 @@ class IndexIVFPQ(IndexIVFFlat):
         raise NotImplementedError("IVF-PQ stores codes only")
 
     def add_codes(self, codes, lists) -> None:
+        self._graphs = {}
         torch = self._torch
         c = torch.as_tensor(np.ascontiguousarray(codes, dtype=np.uint8)).to(self.device)
         l = torch.as_tensor(np.ascontiguousarray(lists, dtype=np.int64)).to(self.device)

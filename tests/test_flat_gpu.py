@@ -357,3 +357,31 @@ def test_dimension_limits(fr):
         fr.FAISSIndex(257, 'Flat')
     with pytest.raises(ValueError, match="multiple of 64"):
         fr.FAISSIndex(100, 'IVFPQ', nlist=4)
+
+
+def test_graph_replay_path_matches_eager(fr, monkeypatch):
+    """Host-result searches of <= 256 queries replay a captured CUDA graph; the answers must be identical to
+    the eager launch sequence, survive new query values / repeated calls, and be re-captured after the corpus
+    changes (add), for every index family."""
+    rng = np.random.default_rng(5)
+    d = 128
+    x = rng.standard_normal((90000, d)).astype(np.float32)
+    for kind in ("Flat", "IVF", "IVFPQ"):
+        g = fr.FAISSIndex(d, kind, nlist=32, nprobe=6, pq_m=16)
+        g.add(x[:60000])
+        for trial in range(3):
+            q = rng.standard_normal((7, d)).astype(np.float32)
+            ids_g, dist_g = g.search(q, k=100)
+            assert any(e for e in g.index._graphs.values()), "graph path was not taken"
+            monkeypatch.setenv("B2R_NO_GRAPHS", "1")
+            ids_e, dist_e = g.search(q, k=100)
+            monkeypatch.delenv("B2R_NO_GRAPHS")
+            assert np.array_equal(ids_g, ids_e) and np.array_equal(dist_g, dist_e), (kind, trial)
+        g.add(x[60000:])                       # corpus changed: stale graphs must go
+        assert not g.index._graphs
+        q = x[60000:60005] + 0.01 * rng.standard_normal((5, d)).astype(np.float32)
+        ids, _ = g.search(q, k=10)
+        if kind != "IVFPQ":
+            assert ids[:, 0].tolist() == list(range(60000, 60005))
+        ids_t, _ = g.search(__import__("torch").from_numpy(q).cuda(), k=10)     # CUDA tensor input, same graph
+        assert np.array_equal(ids, ids_t)
