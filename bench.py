@@ -210,6 +210,7 @@ def run_b200(args):
     if world == 1:
         index = FAISSIndex(D, 'Flat', device=local_rank)   # reference surface: default ids -> device id map
         flat = index.index
+        flat.reserve(total_rows)
         sharded = None
     else:
         sharded = ShardedFlatIndex(D, total_rows, device=local_rank)

@@ -88,6 +88,13 @@ int b2r_index_train(b2r_index* h, int64_t n, const float* x, uint64_t seed, void
  * synchronises the stream when it does. */
 int b2r_index_add(b2r_index* h, int64_t n, const float* x, int normalize, void* stream);
 
+/* Pre-size a FLAT index for `rows` vectors (the `np.vstack` of the whole corpus before
+ * `index.add`, training_pipeline.py:524-531, made explicit): later adds up to that size never
+ * reallocate, so the peak footprint stays at one copy of the corpus (a 50M-row shard is
+ * 77 GB; growing into it would briefly need two).  No-op when already that large or for the
+ * IVF kinds (they re-sort their storage on every add). */
+int b2r_index_reserve(b2r_index* h, int64_t rows, void* stream);
+
 /* Replaces the python id remap loop `id_map[idx]` (faiss_retrieval.py:159-160):
  * ids: int64 [ntotal] device copy of id_map (copied into the handle); search then
  * returns ids[label] (and ids[ntotal-1] for empty slots, the reference's

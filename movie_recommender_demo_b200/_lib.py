@@ -65,6 +65,7 @@ def load():
         "b2r_index_create": (i32, [C.POINTER(vp), i32, i32, i32, i32, i32, i32, i32]),
         "b2r_index_destroy": (i32, [vp]),
         "b2r_index_reset": (i32, [vp]),
+        "b2r_index_reserve": (i32, [vp, i64, vp]),
         "b2r_index_ntotal": (i64, [vp]),
         "b2r_index_is_trained": (i32, [vp]),
         "b2r_index_train": (i32, [vp, i64, vp, C.c_uint64, vp]),

@@ -426,6 +426,21 @@ int b2r_index_destroy(b2r_index* h) {
   return B2R_OK;
 }
 
+int b2r_index_reserve(b2r_index* h, int64_t rows, void* stream) {
+  if (!h) return fail(B2R_EINVAL, "index_reserve: NULL handle");
+  if (rows < 0) return fail(B2R_EINVAL, "index_reserve: negative row count");
+  if (rows > 0x7FFFFF00ll) return fail(B2R_EUNSUPPORTED, "index_reserve: more than 2^31 rows per shard");
+  if (h->kind != B2R_KIND_FLAT) return B2R_OK;
+  DeviceGuard g(h->device);
+  if (rows <= h->capacity) return B2R_OK;
+  // exact size (ensure_capacity over-allocates by 1.5x only when it grows an existing buffer on demand)
+  const int64_t keep = h->capacity;
+  h->capacity = 0;
+  const int rc = ensure_capacity(h, rows, (cudaStream_t)stream);
+  if (rc) h->capacity = keep;
+  return rc;
+}
+
 int b2r_index_reset(b2r_index* h) {
   if (!h) return fail(B2R_EINVAL, "index_reset: NULL handle");
   DeviceGuard g(h->device);

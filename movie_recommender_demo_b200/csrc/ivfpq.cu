@@ -367,13 +367,15 @@ ivfpq_scan_query_kernel(const float* __restrict__ q32, int d, const int64_t* __r
       mbar_wait(bar_full(buf), (uint32_t)(use & 1), 42);
       for (int base = cw * 32; base < nrows; base += kPqConsumers * 32) {
         float a[LR];
+        const uint32_t* twl = tw + base * LR + lane;   // word (row base + ps*RP + rsub, j) = twl[ps * 32]
 #pragma unroll
         for (int ps = 0; ps < LR; ++ps) {
-          const uint32_t w = tw[(base + ps * RP + rsub) * LR + j];   // rows past the list end: stale bytes, discarded
-          float v = lb[0][(w & 255u) * 128];
-          v += lb[1][((w >> 8) & 255u) * 128];
-          v += lb[2][((w >> 16) & 255u) * 128];
-          v += lb[3][(w >> 24) * 128];
+          const uint32_t w = twl[ps * 32];   // rows past the list end: stale bytes, discarded
+          // one PRMT per byte (zero-extended), one IMAD for the address: the loop is issue-bound
+          float v = lb[0][__byte_perm(w, 0u, 0x4440u) * 128];
+          v += lb[1][__byte_perm(w, 0u, 0x4441u) * 128];
+          v += lb[2][__byte_perm(w, 0u, 0x4442u) * 128];
+          v += lb[3][__byte_perm(w, 0u, 0x4443u) * 128];
           a[ps] = v;
         }
         // transposing butterfly over the LR lanes of a row group: lane j ends with the total of pass j

@@ -180,6 +180,12 @@ class _DeviceIndex:
                                                _stream_ptr(self._torch, self.device)))
         self._ids_set = False
 
+    def reserve(self, rows: int) -> None:
+        """Pre-size the corpus buffers (flat index): adds up to `rows` vectors then never reallocate."""
+        self._graphs = {}
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._lib.b2r_index_reserve(self._h, int(rows), _stream_ptr(self._torch, self.device)))
+
     def reset(self) -> None:
         self._graphs = {}
         _lib.check(self._lib.b2r_index_reset(self._h))

@@ -56,6 +56,7 @@ class ShardedFlatIndex:
         self.lo, self.hi = shard_rows(total_rows, self.world, self.rank)
         self.local = self._make_local(device)
         self.local.set_label_base(self.lo)
+        self.local.reserve(self.hi - self.lo)      # one allocation for the whole shard (no growth copies)
         self._torch = torch
 
     def _make_local(self, device):

@@ -385,3 +385,22 @@ def test_graph_replay_path_matches_eager(fr, monkeypatch):
             assert ids[:, 0].tolist() == list(range(60000, 60005))
         ids_t, _ = g.search(__import__("torch").from_numpy(q).cuda(), k=10)     # CUDA tensor input, same graph
         assert np.array_equal(ids, ids_t)
+
+
+def test_reserve_keeps_rows_and_avoids_regrowth(fr):
+    import torch
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((5000, 64)).astype(np.float32)
+    g = fr.FAISSIndex(64, 'Flat')
+    g.add(x[:1000])
+    g.index.reserve(5000)
+    before = torch.cuda.memory_allocated()
+    g.add(x[1000:])
+    assert g.index.ntotal == 5000
+    ids, _ = g.search(x[[3, 4999]], k=1)
+    assert ids[:, 0].tolist() == [3, 4999]
+    g.index.reserve(10)            # smaller than the current size: no-op
+    assert g.index.ntotal == 5000
+    with pytest.raises(Exception):
+        g.index.reserve(-1)
+    assert before >= 0
