@@ -259,7 +259,11 @@ kth_value_small_kernel(const float* __restrict__ vals, int T, int64_t ld, int m,
 //   5. bitonic sort of the window by (-score, row), gather ids, write top-k
 constexpr int kSel2Threads = 1024;
 
-__global__ void __launch_bounds__(kSel2Threads, 2)
+// MINB = CTAs per SM the register budget is sized for: 2 (32 registers) when there are more queries than SMs,
+// 1 (64 registers, all eight loads of a 256-d row in flight per lane) for small batches, where a second
+// resident CTA has nothing to do and the kernel is a pure latency chain.  Same arithmetic order in both.
+template <int MINB>
+__global__ void __launch_bounds__(kSel2Threads, MINB)
 select_rescore_kernel(const SelectParams p) {
   extern __shared__ __align__(16) uint8_t sm[];
   const int kKeyCap = p.key_cap, kRescoreMax = p.rescore_max;             // per-launch capacities
@@ -309,19 +313,35 @@ select_rescore_kernel(const SelectParams p) {
     // without a rescore (IVF-PQ) the scan score is final: key on the LABEL right away, so that the
     // selection below is canonical (score desc, label asc) even among exact ties
     const uint32_t* to_label = p.rescore ? nullptr : p.perm;
-    // a group of G threads copies one segment: a warp when there are many segments (flat scan: one per
-    // corpus split), the whole block when there is one (IVF: a single candidate list per query)
     const int nwarps = blockDim.x >> 5;
-    const int G = p.nseg >= nwarps ? 32 : ((int)blockDim.x / p.nseg) & ~31;
-    const int groups = (int)blockDim.x / G, gid = tid / G, lig = tid % G;
-    if (gid < groups) {
-      for (int sgi = gid; sgi < p.nseg; sgi += groups) {
-        const int pos0 = soff[sgi], n = soff[sgi + 1] - pos0;
-        const uint2* seg = p.cand + ((size_t)q * p.nseg + sgi) * p.cap_seg;
-        for (int i = lig; i < n; i += G) {
-          if (pos0 + i < kKeyCap) {
-            const uint2 e = seg[i];
-            keys[pos0 + i] = make_key(__uint_as_float(e.x), to_label ? to_label[e.y] : e.y);
+    if (p.nseg > nwarps) {
+      // many short segments (flat scan at small batch: ~300 segments of ~4 entries): one thread per
+      // CANDIDATE, its segment found by binary search over the offsets -> every load of the gather is in
+      // flight at once instead of one dependent round trip per segment
+      const int total = s_c < kKeyCap ? s_c : kKeyCap;
+      for (int idx = tid; idx < total; idx += blockDim.x) {
+        int lo = 0, hi = p.nseg - 1;            // largest sgi with soff[sgi] <= idx
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (soff[mid] <= idx) lo = mid; else hi = mid - 1;
+        }
+        const uint2 e = p.cand[((size_t)q * p.nseg + lo) * p.cap_seg + (idx - soff[lo])];
+        keys[idx] = make_key(__uint_as_float(e.x), to_label ? to_label[e.y] : e.y);
+      }
+    } else {
+      // a group of G threads copies one segment: a warp per segment, or the whole block when there is one
+      // (IVF: a single candidate list per query)
+      const int G = p.nseg >= nwarps ? 32 : ((int)blockDim.x / p.nseg) & ~31;
+      const int groups = (int)blockDim.x / G, gid = tid / G, lig = tid % G;
+      if (gid < groups) {
+        for (int sgi = gid; sgi < p.nseg; sgi += groups) {
+          const int pos0 = soff[sgi], n = soff[sgi + 1] - pos0;
+          const uint2* seg = p.cand + ((size_t)q * p.nseg + sgi) * p.cap_seg;
+          for (int i = lig; i < n; i += G) {
+            if (pos0 + i < kKeyCap) {
+              const uint2 e = seg[i];
+              keys[pos0 + i] = make_key(__uint_as_float(e.x), to_label ? to_label[e.y] : e.y);
+            }
           }
         }
       }
@@ -394,7 +414,19 @@ select_rescore_kernel(const SelectParams p) {
       const float4* xp = reinterpret_cast<const float4*>(xbase + (uint64_t)ix * row_bytes) + l8;
       const float4* qp = qv4 + l8;
       float acc = 0.f;
-      if (full) {
+      if (MINB == 1 && nv == 64) {
+        float4 xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) xv[u] = __ldg(xp + u * 8);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4 qq = qp[u * 8];
+          acc = fmaf(xv[u].x, qq.x, acc);
+          acc = fmaf(xv[u].y, qq.y, acc);
+          acc = fmaf(xv[u].z, qq.z, acc);
+          acc = fmaf(xv[u].w, qq.w, acc);
+        }
+      } else if (full) {
 #pragma unroll 1
         for (int t = 0; t < nv; t += 32) {
           float4 xv[4];
@@ -557,11 +589,16 @@ int launch_select_rescore(const SelectParams& p_in, cudaStream_t stream) {
   int dev = 0;
   B2R_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
-    B2R_CUDA(cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B2R_CUDA(cudaFuncSetAttribute(select_rescore_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kKeyCapBig * 8 + kRescoreMaxBig * 8 + 1024 * 4 + 8192 * 4));
+    B2R_CUDA(cudaFuncSetAttribute(select_rescore_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kKeyCapBig * 8 + kRescoreMaxBig * 8 + 1024 * 4 + 8192 * 4));
     configured[dev & 63] = true;
   }
-  select_rescore_kernel<<<p.Q, threads, smem, stream>>>(p);
+  int sms = 0;
+  B2R_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (!small && p.Q <= sms) select_rescore_kernel<1><<<p.Q, threads, smem, stream>>>(p);
+  else select_rescore_kernel<2><<<p.Q, threads, smem, stream>>>(p);
   B2R_CHECK_LAUNCH("select_rescore_kernel");
   return B2R_OK;
 }

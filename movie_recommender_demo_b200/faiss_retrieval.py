@@ -103,6 +103,7 @@ class _DeviceIndex:
         self.last_retries = 0
         self._copy_stream = None
         self._graphs = {}        # (nq, k, normalize, nprobe) -> captured search (small batches), see _graph_entry
+        self.replayed_launches = 0   # kernels launched through graph replays (they bypass the library's own counter)
 
     # ------------------------------------------------------------ lifetime
     def __del__(self):
@@ -303,7 +304,9 @@ class _DeviceIndex:
                     ent["I"].data_ptr(), ent["status"].data_ptr(), ent["tau_retry"].data_ptr(), None,
                     ent["ws"].data_ptr(), ent["ws"].numel(), _stream_ptr(torch, self.device)))
 
+            n0 = int(self._lib.b2r_debug_launch_count())
             launch()    # eager once: one-time kernel attribute set-up must not happen under capture
+            ent["launches"] = int(self._lib.b2r_debug_launch_count()) - n0
             torch.cuda.current_stream(self.device).synchronize()
             graph = torch.cuda.CUDAGraph()
             try:
@@ -317,6 +320,26 @@ class _DeviceIndex:
             self._graphs.pop(next(iter(self._graphs)))
         self._graphs[key] = ent
         return ent
+
+    def search_device_static(self, q, k: int, *, normalize: bool = False, nprobe: int = 0):
+        """Device-resident small-batch search through the captured graph: (D, I, status) are the graph's
+        STATIC output tensors, valid until the next search on this index.  Falls back to `search_device`
+        when the shape is not graph-eligible.  No retry handling: the caller reads `status`."""
+        torch = self._torch
+        nq = len(q)
+        ent = self._graph_entry(nq, int(k), bool(normalize), int(nprobe)) if 0 < nq <= _GRAPH_MAX_Q else None
+        if not ent:
+            D, I, st, _ = self.search_device(q, k, normalize=normalize, nprobe=nprobe)
+            return D, I, st
+        src = q.detach() if isinstance(q, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32))
+        if src.dim() != 2 or src.shape[1] != self.d:
+            raise ValueError(f"search: expected shape [n, {self.d}], got {tuple(src.shape)}")
+        with torch.cuda.device(self.device):
+            buf = ent["q"]
+            (buf if self._dp == self.d else buf[:, :self.d]).copy_(src, non_blocking=True)
+            ent["graph"].replay()
+            self.replayed_launches += ent["launches"]
+        return ent["D"], ent["I"], ent["status"]
 
     def _search_graph(self, ent, x, k, normalize, nprobe):
         torch = self._torch
@@ -336,6 +359,7 @@ class _DeviceIndex:
         with torch.cuda.device(self.device):
             (q if self._dp == self.d else q[:, :self.d]).copy_(src, non_blocking=True)
             ent["graph"].replay()
+            self.replayed_launches += ent["launches"]
             D, I = ent["D"], ent["I"]
             st_h, D_h, I_h = self._to_pinned(ent["status"]), self._to_pinned(D), self._to_pinned(I)
             torch.cuda.current_stream(self.device).synchronize()
