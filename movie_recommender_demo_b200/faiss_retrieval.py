@@ -33,7 +33,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["FAISSIndex", "TwoStageRetriever", "IndexFlatIP", "METRIC_INNER_PRODUCT", "METRIC_L2"]
+__all__ = ["benchmark_faiss_index", "FAISSIndex", "TwoStageRetriever", "IndexFlatIP", "METRIC_INNER_PRODUCT", "METRIC_L2"]
 
 METRIC_INNER_PRODUCT = _lib.METRIC_IP
 METRIC_L2 = _lib.METRIC_L2
@@ -744,3 +744,38 @@ class TwoStageRetriever:
             say(f"Final {stage2_k} ads selected")
             say(f"\n=== Total Time: {stage1_ms + stage2_ms:.2f}ms ===")
             return final_ids, final_scores
+
+
+def benchmark_faiss_index(dimension: int = 256, num_vectors: int = 1000000, num_queries: int = 100, k: int = 100):
+    """Reference surface (faiss_retrieval.py:372-437): time `add` and one `search` call for each index
+    family on standard-normal data and return {index_type: {add_time, search_time_ms, per_query_ms}}.
+    'HNSW' is outside this build's scope and is reported as skipped instead of raising."""
+    say = print if FAISSIndex.verbose else (lambda *a, **kw: None)
+    say("\n=== Benchmarking FAISS Indices ===")
+    say(f"Vectors: {num_vectors}, Queries: {num_queries}, k: {k}, dim: {dimension}\n")
+    rng = np.random.default_rng()
+    vectors = rng.standard_normal((num_vectors, dimension), dtype=np.float32)
+    queries = rng.standard_normal((num_queries, dimension), dtype=np.float32)
+    results = {}
+    for index_type, config in (('Flat', {}), ('IVF', {'nlist': 100, 'nprobe': 10}),
+                               ('IVFPQ', {'nlist': 100, 'nprobe': 10}), ('HNSW', {})):
+        say(f"\nTesting {index_type} index...")
+        try:
+            index = FAISSIndex(dimension=dimension, index_type=index_type, **config)
+        except NotImplementedError as e:
+            say(f"  skipped: {e}")
+            continue
+        t0 = time.time()
+        index.add(vectors)
+        add_time = time.time() - t0
+        t0 = time.time()
+        index.search(queries, k=k)
+        search_ms = (time.time() - t0) * 1000
+        results[index_type] = {'add_time': add_time, 'search_time_ms': search_ms,
+                               'per_query_ms': search_ms / max(num_queries, 1)}
+        say(f"  Add time: {add_time:.2f}s")
+        say(f"  Search time: {search_ms:.2f}ms ({search_ms / max(num_queries, 1):.2f}ms per query)")
+    say("\n=== Benchmark Summary ===")
+    for index_type, m in results.items():
+        say(f"{index_type:10s}: {m['per_query_ms']:.2f}ms per query")
+    return results

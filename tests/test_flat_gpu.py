@@ -404,3 +404,12 @@ def test_reserve_keeps_rows_and_avoids_regrowth(fr):
     with pytest.raises(Exception):
         g.index.reserve(-1)
     assert before >= 0
+
+
+def test_benchmark_faiss_index_surface(fr):
+    """faiss_retrieval.benchmark_faiss_index (reference :372-437): same call, same result keys; HNSW is
+    reported as skipped (documented deviation)."""
+    res = fr.benchmark_faiss_index(dimension=64, num_vectors=20000, num_queries=7, k=10)
+    assert set(res) == {'Flat', 'IVF', 'IVFPQ'}
+    for m in res.values():
+        assert set(m) == {'add_time', 'search_time_ms', 'per_query_ms'} and m['search_time_ms'] > 0
