@@ -584,9 +584,15 @@ ivf_threshold_kernel(const float* __restrict__ scorebuf, int64_t smax, const int
         }
       }
     };
-    for (int i = threadIdx.x; i < T4; i += blockDim.x) {
+    // two vectors in flight per thread (this sweep is the first touch of the run: HBM latency-bound)
+    for (int i = threadIdx.x; i < T4; i += 2 * blockDim.x) {
       const float4 a = row4[i];
+      const int i2 = i + blockDim.x;
+      const bool has_b = i2 < T4;
+      float4 b = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (has_b) b = row4[i2];
       emit(a.x, 4 * i); emit(a.y, 4 * i + 1); emit(a.z, 4 * i + 2); emit(a.w, 4 * i + 3);
+      if (has_b) { emit(b.x, 4 * i2); emit(b.y, 4 * i2 + 1); emit(b.z, 4 * i2 + 2); emit(b.w, 4 * i2 + 3); }
     }
     __syncthreads();
     return s_count;
