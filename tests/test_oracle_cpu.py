@@ -106,3 +106,62 @@ def test_topk_desc_k_larger_than_n():
     D, I = topk_desc(S, 5)
     assert I.tolist() == [[1, 2, 0, -1, -1]] and (D[0, 3:] == NEG_FLT_MAX).all()
     assert recall_at_k(I, I) == 1.0
+
+
+# ---- self-consistency of the IVF / IVF-PQ restatements (they are unpinned against faiss: at least pin them
+# ---- against the definitions they claim to restate)
+def _unit(n, d, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    return x / np.linalg.norm(x, axis=1, keepdims=True)
+
+
+def test_oracle_ivf_probing_every_list_is_the_flat_answer():
+    from oracle.flat import OracleIndexFlatIP
+    from oracle.ivf import OracleIndexIVFFlat
+    x, q = _unit(3000, 32, 1), _unit(9, 32, 2)
+    ivf = OracleIndexIVFFlat(32, 16)
+    ivf.train(x)
+    ivf.add(x)
+    assert ivf.list_sizes().sum() == 3000
+    flat = OracleIndexFlatIP(32)
+    flat.add(x)
+    ivf.nprobe = 16
+    D1, I1 = ivf.search(q, 40)
+    D2, I2 = flat.search(q, 40)
+    assert np.array_equal(I1, I2) and np.allclose(D1, D2, atol=1e-6)
+    # fewer probes: every returned row lies in a probed list, scores are exact, recall can only go down
+    ivf.nprobe = 3
+    D3, I3 = ivf.search(q, 40)
+    probed = ivf.probe(q)
+    for qi in range(len(q)):
+        ok = I3[qi] >= 0
+        assert np.isin(ivf.assign[I3[qi][ok]], probed[qi]).all()
+        assert np.allclose(D3[qi][ok], x[I3[qi][ok]] @ q[qi], atol=1e-6)
+        assert len(set(I3[qi][ok]) & set(I2[qi])) <= 40
+
+
+def test_oracle_ivfpq_adc_is_the_distance_to_the_decoded_vector():
+    """ADC distance = |q - (centroid + decoded residual)|^2 (by-residual, L2), ascending, canonical ties."""
+    from oracle.ivfpq import OracleIndexIVFPQ
+    x, q = _unit(4000, 32, 3), _unit(6, 32, 4)
+    pq = OracleIndexIVFPQ(32, 8, m=4)
+    pq.train(x)
+    pq.add(x)
+    assert pq.codes.shape == (4000, 4) and pq.codebooks.shape == (4, 256, 8)
+    pq.nprobe = 8
+    D, I = pq.search(q, 30)
+    assert (np.diff(D, axis=1) >= 0).all()
+    decoded = pq.centroids[pq.assign] + np.concatenate(
+        [pq.codebooks[s][pq.codes[:, s]] for s in range(4)], axis=1)
+    for qi in range(len(q)):
+        want = ((q[qi][None, :] - decoded[I[qi]]) ** 2).sum(1)
+        assert np.allclose(D[qi], want, rtol=1e-5, atol=1e-6)
+        # nothing outside the result beats the k-th distance (all lists probed)
+        full = ((q[qi][None, :] - decoded) ** 2).sum(1)
+        assert np.sort(full)[29] <= D[qi, 29] + 1e-5
+    # the encoder picks the nearest codeword of every residual sub-vector
+    r = x - pq.centroids[pq.assign]
+    for s in range(4):
+        d2 = ((r[:50, None, s * 8:(s + 1) * 8] - pq.codebooks[s][None]) ** 2).sum(-1)
+        assert np.array_equal(d2.argmin(1), pq.codes[:50, s])
