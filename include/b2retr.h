@@ -111,7 +111,10 @@ int b2r_index_set_label_base(b2r_index* h, int64_t base);
  * rigorous); cand_factor = target candidates per query as a multiple of k (default 4 bf16 /
  * 2.5 fp16); rescore = 0 returns scan scores of the unit-norm query instead of exact fp32;
  * ivf_sample = 1 (default) lets IVF searches estimate the candidate threshold from a score sample
- * with an exact fallback, 0 always runs the exact radix passes (same answers, more sweeps). */
+ * with an exact fallback, 0 always runs the exact radix passes (same answers, more sweeps);
+ * pq_scan_path = 0 (default) picks the query-major ADC scan when pq_m is 8/16/32, 1 forces the older
+ * one-CTA-per-(query,list) kernel (tests compare the two); force_path / dense_budget / profile /
+ * ivf_debug are test and measurement hooks (see csrc/index.cu). */
 int b2r_index_set_param(b2r_index* h, const char* name, double value);
 double b2r_index_get_param(const b2r_index* h, const char* name);
 
