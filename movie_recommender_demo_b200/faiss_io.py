@@ -3,7 +3,10 @@
 
 Covers exactly the three index families the hot path builds: `IndexFlatIP` (fourcc ``IxFI``; ``IxF2`` /
 ``IxFl`` are accepted on read), `IndexIVFFlat` (``IwFl``) and `IndexIVFPQ` (``IwPQ``), each with an
-`ArrayInvertedLists` (``ilar``, ``full`` or ``sprs`` size table) and a flat coarse quantiser.
+`ArrayInvertedLists` (``ilar``, ``full`` or ``sprs`` size table) and a flat coarse quantiser.  An
+`IndexHNSWFlat` file (``IHNf``, faiss_retrieval.py:65-70) can be READ: the neighbour graph is skipped and
+the vectors of its flat storage go into the exact-L2 stand-in (`faiss_retrieval.IndexHNSWFlat`); it is never
+written, because that index builds no graph (`FAISSIndex.save` uses the native container for 'HNSW').
 
 The layout below is restated from faiss's published serialiser (faiss/impl/index_write.cpp, v1.7.x —
 the dependency is pinned only as `faiss-cpu>=1.7.4` in the reference's requirements.txt and is not
@@ -16,6 +19,9 @@ file produced by a real faiss** — `tests/test_oracle_vs_faiss.py` does that wh
     IwFl           : fourcc | ivf header | invlists
     IwPQ           : fourcc | ivf header | u8 by_residual | u64 code_size | u64 d | u64 M | u64 nbits
                      | u64 n_floats | f32[M*ksub*dsub] | invlists
+    IHNf (read)    : fourcc | header | vec<f64> assign_probas | vec<i32> cum_nneighbor_per_level | vec<i32> levels
+                     | vec<u64> offsets | vec<i32> neighbors | i32 entry_point | i32 max_level | i32 efConstruction
+                     | i32 efSearch | i32 upper_beam | <storage index: IxF2>          (vec<T> = u64 n | T[n])
     invlists ilar  : fourcc | u64 nlist | u64 code_size | fourcc full/sprs | u64 len | u64[len] sizes
                      | per non-empty list: u8[n*code_size] codes, i64[n] ids
 
@@ -153,7 +159,26 @@ def _read_index(r: _Reader) -> Dict:
         if h["invlists"]["nlist"] not in (0, h["nlist"]):
             raise FaissFormatError("invlists nlist != index nlist")
         return h
-    raise FaissFormatError(f"unsupported index type fourcc {tag!r} (supported: IxFI/IxF2/IxFl, IwFl, IwPQ)")
+    if tag == "IHNf":
+        h = _read_header(r)
+        r.vector(np.float64)                       # assign_probas
+        cum = r.vector(np.int32)                   # cum_nneighbor_per_level = [0, 2M, 3M, ...]
+        levels = r.vector(np.int32)
+        r.vector(np.uint64)                        # offsets
+        r.vector(np.int32)                         # neighbors (the graph: not needed by an exact scan)
+        r.unpack("i")                              # entry_point
+        r.unpack("i")                              # max_level
+        ef_c, ef_s = r.unpack("i"), r.unpack("i")
+        r.unpack("i")                              # upper_beam
+        storage = _read_index(r)
+        if storage["kind"] != "Flat" or storage["d"] != h["d"] or storage["ntotal"] != h["ntotal"]:
+            raise FaissFormatError("IHNf storage must be a flat index of the same shape")
+        if len(levels) != h["ntotal"]:
+            raise FaissFormatError("IHNf level table length != ntotal")
+        h.update(kind="HNSW", xb=storage["xb"], storage_metric=storage["metric"],
+                 M=int(cum[1]) // 2 if len(cum) > 1 else 32, efConstruction=ef_c, efSearch=ef_s)
+        return h
+    raise FaissFormatError(f"unsupported index type fourcc {tag!r} (supported: IxFI/IxF2/IxFl, IwFl, IwPQ, IHNf)")
 
 
 def parse(data) -> Dict:
@@ -210,6 +235,9 @@ def _w_index(out: BinaryIO, desc: Dict) -> None:
     kind = desc["kind"]
     if kind == "Flat":
         return _w_flat(out, desc)
+    if kind == "HNSW":
+        raise FaissFormatError("an IHNf file needs the neighbour graph, which the exact-scan 'HNSW' index does not "
+                               "build; use the native container")
     if kind not in ("IVF", "IVFPQ"):
         raise FaissFormatError(f"cannot serialise kind {kind!r}")
     out.write(_fourcc("IwFl" if kind == "IVF" else "IwPQ"))
@@ -274,6 +302,9 @@ def describe(index) -> Dict:
     """One of this package's device indexes -> faiss-format description (copies the corpus to the host)."""
     from . import _lib
     d, n = index.d, index.ntotal
+    if type(index).__name__ == "IndexHNSWFlat":
+        raise FaissFormatError("an IHNf file needs the neighbour graph, which the exact-scan 'HNSW' index does not "
+                               "build; use the native container (FAISSIndex.save does)")
     if index.kind == _lib.KIND_FLAT:
         xb = index.reconstruct_n(0, n).cpu().numpy() if n else np.zeros((0, d), np.float32)
         return flat_desc(xb, index.metric)
@@ -303,9 +334,17 @@ def write_index(index, path: str) -> None:
 
 def build(desc: Dict, device=None):
     """faiss-format description -> a device index of this package."""
-    from .faiss_retrieval import IndexFlatIP
+    from .faiss_retrieval import IndexFlatIP, IndexHNSWFlat
     from . import ivf
     kind, d = desc["kind"], desc["d"]
+    if kind == "HNSW":
+        if desc["metric"] != METRIC_L2 or desc["storage_metric"] != METRIC_L2:
+            raise FaissFormatError("IndexHNSWFlat must be METRIC_L2 (faiss_retrieval.py:68 passes no metric)")
+        index = IndexHNSWFlat(d, desc["M"], device=device)
+        index.hnsw.efConstruction, index.hnsw.efSearch = desc["efConstruction"], desc["efSearch"]
+        if desc["ntotal"]:
+            index.add(desc["xb"], normalize=False)      # raises unless the stored rows have unit norm
+        return index
     if kind == "Flat":
         if desc["metric"] != METRIC_INNER_PRODUCT:
             raise FaissFormatError("only inner-product flat indexes are on the hot path (IndexFlatIP)")
@@ -352,4 +391,4 @@ def sniff(path: str) -> str:
         head = f.read(8)
     if head == b"B2RIDX01":
         return "native"
-    return "faiss" if head[:4] in (b"IxFI", b"IxF2", b"IxFl", b"IwFl", b"IwPQ") else "unknown"
+    return "faiss" if head[:4] in (b"IxFI", b"IxF2", b"IxFl", b"IwFl", b"IwPQ", b"IHNf") else "unknown"

@@ -14,7 +14,10 @@ There is no CPU path: without a CUDA device / the built library every call raise
 
 Documented deviations from the reference:
   * `use_gpu` is accepted and ignored - the index is always on the GPU.
-  * 'HNSW' raises NotImplementedError (graph ANN is outside the hot-path scope).
+  * 'HNSW' (faiss_retrieval.py:65-70) is served by an EXACT squared-L2 scan on the flat tcgen05 path
+    (`IndexHNSWFlat` below): same surface and ordering (ascending L2), recall 1.0 instead of the graph's
+    approximation - on a B200 the brute-force scan of 1M x 256 rows (~0.13 ms) is faster than CPU graph
+    traversal, so no graph is built.
   * extra keyword-only constructor arguments with reference-preserving defaults:
     `device`, `pq_m`.
 """
@@ -33,7 +36,8 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["benchmark_faiss_index", "FAISSIndex", "TwoStageRetriever", "IndexFlatIP", "METRIC_INNER_PRODUCT", "METRIC_L2"]
+__all__ = ["benchmark_faiss_index", "FAISSIndex", "TwoStageRetriever", "IndexFlatIP", "IndexHNSWFlat",
+           "METRIC_INNER_PRODUCT", "METRIC_L2"]
 
 METRIC_INNER_PRODUCT = _lib.METRIC_IP
 METRIC_L2 = _lib.METRIC_L2
@@ -489,6 +493,75 @@ class IndexFlatIP(_DeviceIndex):
     metric = METRIC_INNER_PRODUCT
 
 
+class _HNSWParams:
+    """`index.hnsw` of faiss.IndexHNSWFlat: the reference sets efConstruction / efSearch on it
+    (faiss_retrieval.py:69-70).  Kept as plain attributes; an exact scan has no use for them."""
+
+    def __init__(self, M: int):
+        self.M = int(M)
+        self.efConstruction = 40
+        self.efSearch = 16
+
+
+class IndexHNSWFlat(_DeviceIndex):
+    """Stand-in for `faiss.IndexHNSWFlat(d, M)` (faiss_retrieval.py:65-70; faiss default metric L2,
+    distances ascending): an EXACT squared-L2 search.  HNSW approximates the L2 nearest neighbours; this
+    returns them exactly (what HNSW returns at recall 1.0), from the same kernels as `IndexFlatIP`.
+
+    How: every stored row has unit norm (the reference wrapper normalises on add, faiss_retrieval.py:115;
+    a raw `add` of other vectors is rejected), so ||q - x||^2 = ||q||^2 + 1 - 2<q, x> is monotone in the
+    inner product: the flat IP top-k (fp32-rescored, canonical tie order) IS the L2 top-k, and the distances
+    follow from the exact fp32 inner products.  Missing slots: label -1, distance +FLT_MAX as in faiss."""
+    kind = _lib.KIND_FLAT
+    metric = METRIC_INNER_PRODUCT     # metric of the underlying scan; results are reported as L2
+    reported_metric = METRIC_L2
+    _NORM_TOL = 1e-3
+
+    def __init__(self, d: int, M: int = 32, *, device=None):
+        super().__init__(d, device=device)
+        self.hnsw = _HNSWParams(M)
+
+    def add(self, x, normalize: bool = False) -> None:
+        xt = self._to_device_f32(x, "add")
+        if xt.shape[0]:
+            n2 = (xt * xt).sum(dim=1)
+            if normalize:
+                bad = bool((n2 <= 0).any())
+            else:
+                bad = bool(((n2 - 1.0).abs() > self._NORM_TOL).any())
+            if bad:
+                raise ValueError("the exact-L2 'HNSW' index ranks by inner product and therefore needs unit-norm "
+                                 "rows: add through FAISSIndex.add (which normalises, as the reference does) and "
+                                 "do not add zero vectors")
+        super().add(xt if self._dp == self.d else xt[:, :self.d], normalize=normalize)
+
+    def _query_sqnorms(self, x, normalize: bool):
+        torch = self._torch
+        if isinstance(x, torch.Tensor):
+            n2 = (x.detach().to(torch.float32) ** 2).sum(dim=1)
+            n2 = (n2 > 0).to(torch.float32) if normalize else n2
+            return n2
+        a = np.asarray(x, dtype=np.float32)
+        n2 = np.einsum("ij,ij->i", a, a, dtype=np.float32)
+        return (n2 > 0).astype(np.float32) if normalize else n2
+
+    def search(self, x, k: int, *, normalize: bool = False, nprobe: int = 0, return_device: bool = False):
+        S, I = super().search(x, k, normalize=normalize, return_device=return_device)
+        q2 = self._query_sqnorms(x, normalize)
+        if return_device:
+            torch = self._torch
+            q2 = q2.to(S.device) if isinstance(q2, torch.Tensor) else torch.from_numpy(q2).to(S.device)
+            D = torch.clamp(q2[:, None] + 1.0 - 2.0 * torch.where(I < 0, torch.zeros_like(S), S), min=0.0)
+            return torch.where(I < 0, torch.full_like(D, 3.4028234663852886e38), D), I
+        if not isinstance(q2, np.ndarray):
+            q2 = q2.cpu().numpy()
+        missing = I < 0
+        D = np.maximum(q2[:, None] + np.float32(1.0) - np.float32(2.0) * np.where(missing, np.float32(0.0), S),
+                       np.float32(0.0)).astype(np.float32)
+        D[missing] = np.float32(3.4028234663852886e38)
+        return D, I
+
+
 _NATIVE_MAGIC = b"B2RIDX01"
 
 
@@ -523,8 +596,7 @@ class FAISSIndex:
             from . import ivf  # noqa: WPS433 (kept separate: optional index families)
             self.index = ivf.create(self, kind)
         elif kind == 'HNSW':
-            raise NotImplementedError(
-                "index_type='HNSW' is outside the B200 hot-path scope (graph ANN); use 'Flat', 'IVF' or 'IVFPQ'")
+            self.index = IndexHNSWFlat(self.dimension, 32, device=self._device)   # M = 32, efC 40, efS 16 (:67-70)
         else:
             raise ValueError(f"Unknown index type: {self.index_type}")
         self._say(f"Created {self.index_type} index with dimension {self.dimension}")
@@ -609,16 +681,19 @@ class FAISSIndex:
         """Index file + the reference's pickled `.metadata` side-car (same keys as
         faiss_retrieval.py:209-219).  `format="faiss"` (default) writes the `faiss.write_index` layout
         (faiss_io.py) so the file is interchangeable with the reference's; `format="native"` writes
-        this package's own container."""
+        this package's own container.  'HNSW' always uses the native container: a faiss `IHNf` file carries
+        the neighbour graph, which the exact-scan stand-in never builds (reading one works, see `load`)."""
         Path(filepath).parent.mkdir(parents=True, exist_ok=True)
+        if format not in ("faiss", "native"):
+            raise ValueError(f"unknown index file format {format!r}")
+        if self.index_type == 'HNSW':
+            format = "native"
         if format == "faiss":
             from . import faiss_io
             self.index.nprobe = self.nprobe
             faiss_io.write_index(self.index, filepath)
-        elif format == "native":
-            self._save_native(filepath)
         else:
-            raise ValueError(f"unknown index file format {format!r}")
+            self._save_native(filepath)
         with open(filepath + '.metadata', 'wb') as f:
             pickle.dump({'dimension': self.dimension, 'index_type': self.index_type, 'nlist': self.nlist,
                          'nprobe': self.nprobe, 'id_map': list(self.id_map)}, f)
@@ -652,7 +727,8 @@ class FAISSIndex:
         layout = faiss_io.sniff(filepath)
         if layout == "faiss":
             index = faiss_io.read_index(filepath, device=self._device)
-            want = {'Flat': 'IndexFlatIP', 'IVF': 'IndexIVFFlat', 'IVFPQ': 'IndexIVFPQ'}.get(self.index_type)
+            want = {'Flat': 'IndexFlatIP', 'IVF': 'IndexIVFFlat', 'IVFPQ': 'IndexIVFPQ',
+                    'HNSW': 'IndexHNSWFlat'}.get(self.index_type)
             if type(index).__name__ != want:
                 raise ValueError(f"{filepath}: holds a {type(index).__name__}, metadata says {self.index_type}")
             if index.d != self.dimension:
@@ -662,7 +738,7 @@ class FAISSIndex:
         elif layout == "native":
             self._load_native(filepath)
         else:
-            raise ValueError(f"{filepath}: neither a faiss index file (IxFI/IwFl/IwPQ) nor a b200 native container")
+            raise ValueError(f"{filepath}: neither a faiss index file (IxFI/IwFl/IwPQ/IHNf) nor a b200 native container")
         self.id_map = list(meta['id_map'])
         self._ids_all_int = all(isinstance(a, (int, np.integer)) for a in self.id_map)
         self._sync_ids()
@@ -748,8 +824,7 @@ class TwoStageRetriever:
 
 def benchmark_faiss_index(dimension: int = 256, num_vectors: int = 1000000, num_queries: int = 100, k: int = 100):
     """Reference surface (faiss_retrieval.py:372-437): time `add` and one `search` call for each index
-    family on standard-normal data and return {index_type: {add_time, search_time_ms, per_query_ms}}.
-    'HNSW' is outside this build's scope and is reported as skipped instead of raising."""
+    family on standard-normal data and return {index_type: {add_time, search_time_ms, per_query_ms}}."""
     say = print if FAISSIndex.verbose else (lambda *a, **kw: None)
     say("\n=== Benchmarking FAISS Indices ===")
     say(f"Vectors: {num_vectors}, Queries: {num_queries}, k: {k}, dim: {dimension}\n")
@@ -760,11 +835,7 @@ def benchmark_faiss_index(dimension: int = 256, num_vectors: int = 1000000, num_
     for index_type, config in (('Flat', {}), ('IVF', {'nlist': 100, 'nprobe': 10}),
                                ('IVFPQ', {'nlist': 100, 'nprobe': 10}), ('HNSW', {})):
         say(f"\nTesting {index_type} index...")
-        try:
-            index = FAISSIndex(dimension=dimension, index_type=index_type, **config)
-        except NotImplementedError as e:
-            say(f"  skipped: {e}")
-            continue
+        index = FAISSIndex(dimension=dimension, index_type=index_type, **config)
         t0 = time.time()
         index.add(vectors)
         add_time = time.time() - t0

@@ -11,6 +11,12 @@ Follows, in order of operations:
         len(id_map), id remap `id_map[idx]` with python negative-index wrap for -1,
         return order (ad_ids, distances).
 
+  * `faiss.IndexHNSWFlat(d, 32)`               faiss_retrieval.py:65-70
+        default metric L2, distances ascending.  HNSW is an APPROXIMATION of the exact L2 nearest
+        neighbours whose graph depends on faiss's RNG and insertion threading, so it has no reproducible
+        answer of its own; its oracle is the thing it approximates: exact fp32 ||q - x||^2, top-k smallest
+        (`OracleIndexFlatL2`), missing slots label -1 / distance +3.4028235e38.
+
 faiss's order among exactly equal scores is implementation-defined; the oracle's canonical
 order is (-score, label).  PARITY UNPINNED against faiss itself (see oracle/__init__.py).
 """
@@ -85,6 +91,25 @@ class OracleIndexFlatIP:
         return topk_desc(self.scores(q), k, extra)
 
 
+class OracleIndexFlatL2(OracleIndexFlatIP):
+    """Exact squared-L2 search (what `faiss.IndexHNSWFlat` approximates): direct fp32 sum of squared
+    differences, top-k smallest in canonical (distance, label) order."""
+
+    def distances(self, q: np.ndarray) -> np.ndarray:
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        out = np.empty((q.shape[0], self.ntotal), dtype=np.float32)
+        for i in range(q.shape[0]):
+            diff = self.xb - q[i]
+            out[i] = np.einsum("ij,ij->i", diff, diff, dtype=np.float32)
+        return out
+
+    def search(self, q: np.ndarray, k: int, extra: int = 0):
+        D, I = topk_desc(-self.distances(q), k, extra)
+        D = -D
+        D[I < 0] = -NEG_FLT_MAX
+        return D, I
+
+
 class OracleFAISSIndex:
     """The reference's `FAISSIndex` wrapper (faiss_retrieval.py:14-256) over oracle indexes."""
 
@@ -103,6 +128,8 @@ class OracleFAISSIndex:
         elif index_type == 'IVFPQ':
             from .ivfpq import OracleIndexIVFPQ
             self.index = OracleIndexIVFPQ(dimension, nlist, kw.pop('pq_m', 8), 8, **kw)
+        elif index_type == 'HNSW':
+            self.index = OracleIndexFlatL2(dimension)
         else:
             raise ValueError(f"Unknown index type: {self.index_type}")
 

@@ -1,6 +1,7 @@
 """faiss index file layout (movie_recommender_demo_b200/faiss_io.py), host-only layer: parse/serialize.
 The expected bytes below are assembled by hand from the published layout (faiss/impl/index_write.cpp),
 not by the code under test."""
+import io
 import struct
 
 import numpy as np
@@ -77,9 +78,43 @@ def test_ivfpq_round_trip_and_pq_block():
     assert fio.serialize(back) == blob            # idempotent
 
 
+def _hnsw_file(xb, M=32, ef_c=40, ef_s=16, storage_metric=1):
+    """An `IndexHNSWFlat` file authored from the published layout (header, HNSW block, flat L2 storage);
+    the graph arrays hold plausible sizes and arbitrary contents - an exact scan never looks at them."""
+    n, d = xb.shape
+    out = io.BytesIO()
+    out.write(b"IHNf")
+    out.write(struct.pack("<iqqqBi", d, n, 1 << 20, 1 << 20, 1, 1))
+    def vec(a):
+        a = np.ascontiguousarray(a)
+        out.write(struct.pack("<Q", a.size))
+        out.write(a.tobytes())
+    vec(np.array([0.9, 0.09, 0.01], np.float64))                   # assign_probas
+    vec(np.array([0, 2 * M, 3 * M, 4 * M], np.int32))              # cum_nneighbor_per_level
+    vec(np.ones(n, np.int32))                                      # levels
+    vec(np.arange(n + 1, dtype=np.uint64) * (2 * M))               # offsets
+    vec(np.full(n * 2 * M, -1, np.int32))                          # neighbors
+    out.write(struct.pack("<iiiii", 0, 0, ef_c, ef_s, 1))          # entry_point, max_level, efC, efS, upper_beam
+    out.write(fio.serialize(fio.flat_desc(xb, storage_metric)))
+    return out.getvalue()
+
+
+def test_hnsw_file_is_read_as_vectors_plus_parameters():
+    rng = np.random.default_rng(5)
+    xb = rng.standard_normal((37, 12)).astype(np.float32)
+    desc = fio.parse(_hnsw_file(xb, M=16, ef_c=55, ef_s=21))
+    assert desc["kind"] == "HNSW" and desc["metric"] == 1 and desc["storage_metric"] == 1
+    assert desc["M"] == 16 and desc["efConstruction"] == 55 and desc["efSearch"] == 21
+    assert np.array_equal(desc["xb"], xb)
+    with pytest.raises(fio.FaissFormatError, match="neighbour graph"):
+        fio.serialize(desc)                                        # never written: there is no graph to write
+    with pytest.raises(fio.FaissFormatError, match="truncated"):
+        fio.parse(_hnsw_file(xb)[:-3])
+
+
 def test_reader_rejects_what_it_cannot_represent(tmp_path):
     with pytest.raises(fio.FaissFormatError, match="unsupported index type"):
-        fio.parse(b"IHNf" + b"\0" * 64)
+        fio.parse(b"IHNs" + b"\0" * 64)
     good = fio.serialize(fio.flat_desc(np.ones((3, 4), np.float32)))
     with pytest.raises(fio.FaissFormatError, match="truncated"):
         fio.parse(good[:-5])

@@ -407,9 +407,69 @@ def test_reserve_keeps_rows_and_avoids_regrowth(fr):
 
 
 def test_benchmark_faiss_index_surface(fr):
-    """faiss_retrieval.benchmark_faiss_index (reference :372-437): same call, same result keys; HNSW is
-    reported as skipped (documented deviation)."""
+    """faiss_retrieval.benchmark_faiss_index (reference :372-437): same call, same result keys for the
+    four index families."""
     res = fr.benchmark_faiss_index(dimension=64, num_vectors=20000, num_queries=7, k=10)
-    assert set(res) == {'Flat', 'IVF', 'IVFPQ'}
+    assert set(res) == {'Flat', 'IVF', 'IVFPQ', 'HNSW'}
     for m in res.values():
         assert set(m) == {'add_time', 'search_time_ms', 'per_query_ms'} and m['search_time_ms'] > 0
+
+
+@pytest.mark.parametrize("N,Q,k,d", [(30000, 9, 100, 256), (120000, 40, 500, 128), (300, 3, 500, 100)])
+def test_hnsw_type_is_an_exact_l2_search(fr, N, Q, k, d, tmp_path):
+    """index_type='HNSW' (faiss_retrieval.py:65-70: IndexHNSWFlat, L2, ascending): served by the exact scan,
+    so it must equal the exact L2 oracle (= what HNSW approximates; recall 1.0), ids first, ascending
+    distances, +FLT_MAX / id_map[-1] in unfilled slots, and survive save -> load."""
+    from oracle.compare import compare_topk
+    from oracle.flat import OracleFAISSIndex
+    rng = np.random.default_rng(N)
+    x = rng.standard_normal((N, d)).astype(np.float32)
+    q = rng.standard_normal((Q, d)).astype(np.float32)
+    g = fr.FAISSIndex(d, 'HNSW')
+    assert (g.index.hnsw.M, g.index.hnsw.efConstruction, g.index.hnsw.efSearch) == (32, 40, 16)
+    assert g.index.is_trained and not hasattr(g.index, "nprobe")
+    ids0 = [7 * i + 1 for i in range(N)]
+    g.add(x, ids0)
+    o = OracleFAISSIndex(d, 'HNSW')
+    o.add(x, ids0)
+    ids, dist = g.search(q, k=k)
+    rid, rd = o.search(q, k=k, extra=32 if N > k + 32 else 0)
+    assert (np.diff(dist[:, :min(k, N)], axis=1) >= 0).all()
+    compare_topk(ids, dist, rid, rd, k, gap_tol=4e-6, score_rtol=1e-4, score_atol=4e-6, descending=False)
+    if N < k:                                   # under-filled: faiss gives (-1, +FLT_MAX); wrapper maps -1 -> id_map[-1]
+        assert np.array_equal(ids[:, :N], rid[:, :N])
+        assert (ids[:, N:] == ids0[-1]).all() and (dist[:, N:] == np.float32(3.4028234663852886e38)).all()
+    p = str(tmp_path / "hnsw.index")
+    g.save(p)                                   # native container (no graph to put in an IHNf file)
+    g2 = fr.FAISSIndex(d, 'Flat')
+    g2.load(p)
+    assert g2.index_type == 'HNSW' and type(g2.index).__name__ == 'IndexHNSWFlat' and g2.index.ntotal == N
+    ids2, dist2 = g2.search(q, k=k)
+    assert np.array_equal(ids, ids2) and np.array_equal(dist, dist2)
+
+
+def test_hnsw_rejects_rows_it_cannot_rank_and_reads_faiss_files(fr, tmp_path):
+    import pickle
+    from test_faiss_io_cpu import _hnsw_file
+    rng = np.random.default_rng(3)
+    h = fr.IndexHNSWFlat(64)
+    with pytest.raises(ValueError, match="unit-norm"):
+        h.add(rng.standard_normal((10, 64)).astype(np.float32))              # raw add of un-normalised rows
+    with pytest.raises(ValueError, match="unit-norm"):
+        h.add(np.zeros((2, 64), np.float32), normalize=True)                 # zero rows cannot be normalised
+    assert h.ntotal == 0
+    # an IndexHNSWFlat file authored from the published layout: vectors are taken, the graph is skipped
+    x = rng.standard_normal((5000, 64)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    p = tmp_path / "ref_hnsw.index"
+    p.write_bytes(_hnsw_file(x, M=32))
+    with open(str(p) + ".metadata", "wb") as f:
+        pickle.dump({'dimension': 64, 'index_type': 'HNSW', 'nlist': 100, 'nprobe': 10,
+                     'id_map': list(range(5000))}, f)
+    g = fr.FAISSIndex(64, 'Flat')
+    g.load(str(p))
+    assert g.index_type == 'HNSW' and g.index.ntotal == 5000 and g.index.hnsw.M == 32
+    ids, dist = g.search(x[[11, 4321]], k=5)
+    assert ids[:, 0].tolist() == [11, 4321] and np.allclose(dist[:, 0], 0.0, atol=2e-6)
+    want = np.sort(((x[11][None] - x) ** 2).sum(1))[:5]
+    assert np.allclose(dist[0], want, atol=4e-6)

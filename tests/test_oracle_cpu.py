@@ -165,3 +165,23 @@ def test_oracle_ivfpq_adc_is_the_distance_to_the_decoded_vector():
     for s in range(4):
         d2 = ((r[:50, None, s * 8:(s + 1) * 8] - pq.codebooks[s][None]) ** 2).sum(-1)
         assert np.array_equal(d2.argmin(1), pq.codes[:50, s])
+
+
+def test_oracle_hnsw_stand_in_is_exact_l2():
+    """'HNSW' (faiss_retrieval.py:65-70, L2) is checked against the exact L2 answer it approximates: on
+    unit-norm rows that is the Flat IP ranking with distance 2 - 2<q,x>; ascending; empty slots +FLT_MAX."""
+    from oracle.flat import OracleFAISSIndex
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((700, 24)).astype(np.float32)
+    q = rng.standard_normal((5, 24)).astype(np.float32)
+    h, f = OracleFAISSIndex(24, 'HNSW'), OracleFAISSIndex(24, 'Flat')
+    h.add(x), f.add(x)
+    ih, dh = h.search(q, k=710)
+    i_f, df = f.search(q, k=710)
+    assert np.array_equal(ih[:, :700], i_f[:, :700])
+    assert np.allclose(dh[:, :700], 2 - 2 * df[:, :700], atol=2e-6)
+    assert (np.diff(dh[:, :700], axis=1) >= 0).all()
+    assert (dh[:, 700:] == np.float32(3.4028234663852886e38)).all() and (ih[:, 700:] == 699).all()  # id_map[-1]
+    brute = ((q[:, None, :] / np.linalg.norm(q, axis=1)[:, None, None]
+              - (x / np.linalg.norm(x, axis=1, keepdims=True))[None]) ** 2).sum(-1)
+    assert np.array_equal(np.argsort(brute, axis=1, kind="stable")[:, :50], ih[:, :50])
