@@ -551,11 +551,12 @@ class IndexHNSWFlat(_DeviceIndex):
         if return_device:
             torch = self._torch
             q2 = q2.to(S.device) if isinstance(q2, torch.Tensor) else torch.from_numpy(q2).to(S.device)
-            D = torch.clamp(q2[:, None] + 1.0 - 2.0 * torch.where(I < 0, torch.zeros_like(S), S), min=0.0)
-            return torch.where(I < 0, torch.full_like(D, 3.4028234663852886e38), D), I
+            missing = S <= -3.0e38      # unfilled slot (-FLT_MAX); its label may already be id_map[-1]
+            D = torch.clamp(q2[:, None] + 1.0 - 2.0 * torch.where(missing, torch.zeros_like(S), S), min=0.0)
+            return torch.where(missing, torch.full_like(D, 3.4028234663852886e38), D), I
         if not isinstance(q2, np.ndarray):
             q2 = q2.cpu().numpy()
-        missing = I < 0
+        missing = S <= np.float32(-3.0e38)   # unfilled slot (-FLT_MAX); its label may already be id_map[-1]
         D = np.maximum(q2[:, None] + np.float32(1.0) - np.float32(2.0) * np.where(missing, np.float32(0.0), S),
                        np.float32(0.0)).astype(np.float32)
         D[missing] = np.float32(3.4028234663852886e38)
