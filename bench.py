@@ -394,6 +394,8 @@ def run_b200(args):
             "e2e": None if e2e_value is None else {"value": e2e_value, "unit": "queries/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * K_TOP * 12 + Q * 4},
             "gpu_launches": launches,
+            # workload-independent rate (the N=1 and N>1 configs differ in corpus size): query x row scores per second
+            "scan_throughput": {"value": value * total_rows, "unit": "query*rows/s"},
             "roofline": roof,
             "cpu_baseline": cpu,
             "clocks": clocks,
