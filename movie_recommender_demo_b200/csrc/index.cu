@@ -187,10 +187,10 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
   const int qpad = QG * MQ * kQBlock;  // <= pl.qpad
   const int fp16 = h->scan_fp16 == 1;
   const float eps = (float)(fp16 ? h->eps_fp16 : h->eps);
-  if ((rc = launch_prep_queries(queries, q, qpad, d, normalize, q32, q16, fp16, qnorm, stream))) return rc;
+  // tau[0, qpad) = +inf is written by the same launch (padding queries must never produce candidates)
+  if ((rc = launch_prep_queries(queries, q, qpad, d, normalize, q32, q16, fp16, qnorm, stream, tau))) return rc;
   CUtensorMap tmQ;
   if ((rc = make_tmap_bf16_rows(&tmQ, q16, qpad, d))) return rc;
-  if ((rc = launch_fill_f32(tau, qpad, INFINITY, stream))) return rc;
 
   ScanParams sp;
   memset(&sp, 0, sizeof(sp));

@@ -38,7 +38,8 @@ __device__ __forceinline__ uint32_t pack16x2(float a, float b, int fp16) {
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 normalize_rows_kernel(const float* __restrict__ x, int64_t rows_in, int64_t rows_out, int d,
                       int normalize, float* __restrict__ out32, __nv_bfloat16* __restrict__ out16,
-                      int fp16, int scan16_unit, float* __restrict__ norms, float* __restrict__ maxnorm) {
+                      int fp16, int scan16_unit, float* __restrict__ norms, float* __restrict__ maxnorm,
+                      float* __restrict__ inf_fill) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows_out) return;
@@ -81,6 +82,7 @@ normalize_rows_kernel(const float* __restrict__ x, int64_t rows_in, int64_t rows
     }
   }
   if (lane == 0) {
+    if (inf_fill) inf_fill[row] = INFINITY;  // per-query threshold starts at +inf (padding rows keep it)
     if (norms) norms[row] = (row < rows_in) ? stored_norm : 0.f;
     if (maxnorm && row < rows_in && stored_norm > 0.f && stored_norm < INFINITY)
       atomicMax(reinterpret_cast<int*>(maxnorm), __float_as_int(stored_norm));
@@ -110,7 +112,7 @@ int launch_reencode(const float* x32, int64_t n, int d, __nv_bfloat16* out16, in
   if (n <= 0) return B2R_OK;
   const int64_t blocks = ceil_div(n, kWarpsPerBlock);
   normalize_rows_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(x32, n, n, d, 0, nullptr, out16, fp16, 0,
-                                                                             nullptr, nullptr);
+                                                                             nullptr, nullptr, nullptr);
   B2R_CHECK_LAUNCH("normalize_rows_kernel(reencode)");
   return B2R_OK;
 }
@@ -121,18 +123,18 @@ int launch_ingest(const float* x, int64_t n, int d, int normalize, float* out32,
   if (d % 4 != 0 || d > 1024) return fail(B2R_EINVAL, "ingest: d must be a multiple of 4, <= 1024");
   const int64_t blocks = ceil_div(n, kWarpsPerBlock);
   normalize_rows_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(
-      x, n, n, d, normalize, out32, out16, fp16, 0, nullptr, maxnorm);
+      x, n, n, d, normalize, out32, out16, fp16, 0, nullptr, maxnorm, nullptr);
   B2R_CHECK_LAUNCH("normalize_rows_kernel");
   return B2R_OK;
 }
 
 int launch_prep_queries(const float* x, int q, int qpad, int d, int normalize, float* q32,
-                        __nv_bfloat16* q16, int fp16, float* qnorm, cudaStream_t stream) {
+                        __nv_bfloat16* q16, int fp16, float* qnorm, cudaStream_t stream, float* tau_init) {
   if (qpad <= 0) return B2R_OK;
   if (d % 4 != 0 || d > 1024) return fail(B2R_EINVAL, "queries: d must be a multiple of 4, <= 1024");
   const int64_t blocks = ceil_div(qpad, kWarpsPerBlock);
   normalize_rows_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(
-      x, q, qpad, d, normalize, q32, q16, fp16, 1, qnorm, nullptr);
+      x, q, qpad, d, normalize, q32, q16, fp16, 1, qnorm, nullptr, tau_init);
   B2R_CHECK_LAUNCH("normalize_rows_kernel(queries)");
   return B2R_OK;
 }

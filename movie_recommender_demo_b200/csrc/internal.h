@@ -93,9 +93,11 @@ void plan_scan(int Q, int tile_count, int num_sms, int* MQ, int* QG, int* splits
 int launch_ingest(const float* x, int64_t n, int d, int normalize, float* out32,
                   __nv_bfloat16* out16, int fp16, float* maxnorm, cudaStream_t stream);
 // queries fp32 [q,d] -> q32 [qpad,d] (normalised iff `normalize`), q16 [qpad,d] = ALWAYS unit-norm
-// 16-bit scan copy (zero padded), qnorm [qpad] = norm of the scan copy (1, or 0 for a zero query)
+// 16-bit scan copy (zero padded), qnorm [qpad] = norm of the scan copy (1, or 0 for a zero query);
+// tau_init (optional) [qpad] is set to +inf in the same launch (the per-query threshold's start value)
 int launch_prep_queries(const float* x, int q, int qpad, int d, int normalize, float* q32,
-                        __nv_bfloat16* q16, int fp16, float* qnorm, cudaStream_t stream);
+                        __nv_bfloat16* q16, int fp16, float* qnorm, cudaStream_t stream,
+                        float* tau_init = nullptr);
 // re-encode the 16-bit scan copy of n rows from the fp32 master
 int launch_reencode(const float* x32, int64_t n, int d, __nv_bfloat16* out16, int fp16, cudaStream_t stream);
 uint32_t scan_idesc(int fp16);
