@@ -209,7 +209,8 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
   sp.splits = splits;
   sp.cand_count = count;
   sp.cand = cand;
-  sp.nseg = splits * (MQ == 1 ? 2 : 1);
+  const int epi_warps = (MQ == 2 && h->epi_warps == 16) ? 16 : 8;
+  sp.nseg = splits * ((MQ == 1 || epi_warps == 16) ? 2 : 1);
   sp.cap_seg = pl.cap_seg;
   int sel_nseg = sp.nseg, sel_cap_seg = pl.cap_seg;
 
@@ -243,7 +244,7 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
   if (tau_in || !pl.dense) {
     const bool prof = h->profile && h->prof_used + 2 <= h->prof_ev.size();
     if (prof) cudaEventRecord(h->prof_ev[h->prof_used], stream);
-    if ((rc = launch_scan(SCAN_FILTER, MQ, tmQ, h->tmX, sp, h->num_sms, stream))) return rc;
+    if ((rc = launch_scan(SCAN_FILTER, MQ, tmQ, h->tmX, sp, h->num_sms, stream, epi_warps))) return rc;
     if (prof) {
       cudaEventRecord(h->prof_ev[h->prof_used + 1], stream);
       h->prof_used += 2;
@@ -518,6 +519,10 @@ int b2r_index_set_param(b2r_index* h, const char* name, double value) {
     if (c < 64 || c > 4096 || (c & (c - 1))) return fail(B2R_EINVAL, "cand_cap must be a power of two in [64,4096]");
     h->cand_cap = c;
   }
+  else if (n == "epi_warps") {
+    if (value != 8 && value != 16) return fail(B2R_EINVAL, "epi_warps must be 8 or 16");
+    h->epi_warps = (int)value;
+  }
   else if (n == "rescore") h->rescore = value != 0;
   else if (n == "force_path") h->force_path = (int)value;
   else if (n == "dense_budget") h->dense_budget = (int64_t)value;
@@ -547,6 +552,7 @@ double b2r_index_get_param(const b2r_index* h, const char* name) {
   if (n == "scan_dtype") return h->scan_fp16;
   if (n == "cand_factor") return h->cand_factor;
   if (n == "cand_cap") return h->cand_cap;
+  if (n == "epi_warps") return h->epi_warps;
   if (n == "rescore") return h->rescore;
   if (n == "force_path") return h->force_path;
   if (n == "dense_budget") return (double)h->dense_budget;

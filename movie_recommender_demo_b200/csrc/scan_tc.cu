@@ -12,10 +12,15 @@
 // Queries sit on the lane side so that each epilogue thread owns ONE query: its candidate
 // threshold is a scalar register and the per-score work is a 3-input max plus a rare branch.
 //
-// Warp roles (384 threads, 1 CTA/SM, persistent over "units" = (corpus split, query group)):
+// Warp roles (128 + 32*EW threads, 1 CTA/SM, persistent over "units" = (corpus split, query group)):
 //   warp 0 lane 0 : TMA producer       warp 1 lane 0 : tcgen05.mma issuer
 //   warp 2        : TMEM alloc/dealloc  warp 3        : idle
-//   warps 4..11   : epilogue (tcgen05.ld 32x32b.x32 -> registers), TMEM quarter = warp % 4
+//   warps 4..4+EW : epilogue (tcgen05.ld 32x32b.x32 -> registers), TMEM quarter = warp % 4
+// EW = 8 epilogue warps by default.  With two query blocks (MQ = 2) each of those warps walks all 128
+// columns of its block; under a realistic hit rate (~0.1 % of the scores pass the threshold) that
+// serial instruction stream (~550 instructions per tile at ~6 cycles each) is as long as the tile's MMA
+// time, so the FILTER mode also exists with EW = 16: two warps per (query block, lane quarter), each
+// owning one 64-column half and its own candidate segment.
 //
 // Epilogue modes:
 //   SCAN_DUMP   : store every score                     (tests, small-corpus dense path)
@@ -38,7 +43,6 @@ struct ScanCfg {
   static constexpr int SMEM = 1024 + A_BYTES + B_BYTES + NBARS * 8 + 64;
 };
 
-constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;
 
 template <int MODE>
@@ -101,8 +105,8 @@ __device__ __forceinline__ void epi_chunk(const ScanParams& p, const uint32_t (&
   }
 }
 
-template <int MQ, int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int MQ, int MODE, int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX,
                const ScanParams p) {
   using Cfg = ScanCfg<MQ>;
@@ -133,7 +137,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     for (int i = 0; i < NB; ++i) {
       mbar_init(bar_tfull(i), 1);
-      mbar_init(bar_tempty(i), 8);  // one arrive per epilogue warp
+      mbar_init(bar_tempty(i), EW);  // one arrive per epilogue warp
     }
     mbar_init(bar_qfull, 1);
     mbar_init(bar_qempty, 1);
@@ -243,9 +247,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int e = warp - kEpiWarp0;
     const int quarter = e & 3;  // == warp % 4: the TMEM lane quarter this warp may read
     const int g = e >> 2;
-    const int h = (MQ == 2) ? g : 0;
-    const int col_begin = (MQ == 2) ? 0 : g * 64;
-    constexpr int NCH = (MQ == 2) ? 4 : 2;  // 32-column chunks per tile for this warp
+    // a warp owns (query block h, 64-column half) when the columns are split, else (block h, all 128 columns)
+    constexpr bool kSplitCols = (MQ == 1) || (EW == 16);
+    const int h = (MQ == 2) ? (g & 1) : 0;
+    const int colhalf = (MQ == 2) ? (g >> 1) : g;
+    const int col_begin = kSplitCols ? colhalf * 64 : 0;
+    constexpr int NCH = kSplitCols ? 2 : 4;  // 32-column chunks per tile for this warp
     int tb = 0;
     uint32_t tph = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -254,7 +261,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int j1 = (int)((int64_t)(split + 1) * p.tile_count / p.splits);
       const int q = (qg * MQ + h) * kQBlock + quarter * 32 + lane;
       // this warp's private candidate segment for (query q, split[, column half g])
-      const int segi = (MQ == 2) ? split : split * 2 + g;
+      const int segi = kSplitCols ? split * 2 + colhalf : split;
       uint2* seg = nullptr;
       int cnt = 0;
       if (MODE == SCAN_FILTER) seg = p.cand + ((size_t)q * p.nseg + segi) * p.cap_seg;
@@ -333,10 +340,10 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int MQ, int MODE>
+template <int MQ, int MODE, int EW = 8>
 int launch_one(const CUtensorMap& tmQ, const CUtensorMap& tmX, const ScanParams& p, int grid,
                cudaStream_t stream) {
-  auto kern = scan_tc_kernel<MQ, MODE>;
+  auto kern = scan_tc_kernel<MQ, MODE, EW>;
   static bool configured[64] = {};  // per instantiation, per device
   int dev = 0;
   B2R_CUDA(cudaGetDevice(&dev));
@@ -345,7 +352,7 @@ int launch_one(const CUtensorMap& tmQ, const CUtensorMap& tmX, const ScanParams&
                                   ScanCfg<MQ>::SMEM));
     configured[dev & 63] = true;
   }
-  kern<<<grid, kThreads, ScanCfg<MQ>::SMEM, stream>>>(tmQ, tmX, p);
+  kern<<<grid, 128 + 32 * EW, ScanCfg<MQ>::SMEM, stream>>>(tmQ, tmX, p);
   B2R_CHECK_LAUNCH("scan_tc_kernel");
   return B2R_OK;
 }
@@ -391,12 +398,14 @@ void plan_scan(int Q, int tile_count, int num_sms, int* MQ, int* QG, int* splits
 }
 
 int launch_scan(int mode, int MQ, const CUtensorMap& tmQ, const CUtensorMap& tmX,
-                const ScanParams& p, int num_sms, cudaStream_t stream) {
+                const ScanParams& p, int num_sms, cudaStream_t stream, int epi_warps) {
   if (p.d % kKChunk != 0 || p.d < kKChunk || p.d > 256)
     return fail(B2R_EINVAL, "scan: d must be a multiple of 64 in [64,256]");
   if (p.tile_count <= 0 || p.Q <= 0) return B2R_OK;
   const int64_t units = (int64_t)p.splits * p.QG;
   const int grid = (int)(units < num_sms ? units : num_sms);
+  if (MQ == 2 && mode == SCAN_FILTER && epi_warps == 16)
+    return launch_one<2, SCAN_FILTER, 16>(tmQ, tmX, p, grid, stream);
 #define B2R_SCAN_CASE(MQ_, MODE_)                                             \
   if (MQ == MQ_ && mode == MODE_) return launch_one<MQ_, MODE_>(tmQ, tmX, p, grid, stream);
   B2R_SCAN_CASE(1, SCAN_DUMP)

@@ -23,7 +23,7 @@ def _bf16(a):
     return torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).to(torch.float32).numpy()
 
 
-def _parity(fr, N, Q, k, d=256, seed=0, force_path=0, unit=False):
+def _parity(fr, N, Q, k, d=256, seed=0, force_path=0, unit=False, epi_warps=0):
     from oracle.compare import compare_topk
     from oracle.flat import OracleFAISSIndex
     rng = np.random.default_rng(seed)
@@ -32,6 +32,8 @@ def _parity(fr, N, Q, k, d=256, seed=0, force_path=0, unit=False):
     g = fr.FAISSIndex(d, 'Flat')
     if force_path:
         g.index.set_param("force_path", force_path)
+    if epi_warps:
+        g.index.set_param("epi_warps", epi_warps)
     g.add(x)
     o = OracleFAISSIndex(d, 'Flat')
     o.add(x)
@@ -156,6 +158,14 @@ def test_config1_shape_100k_ads_512_queries_top500(fr):
                                           (600000, 300, 500, 0), (150000, 3, 10, 2)])
 def test_filter_path_matches_oracle(fr, N, Q, k, force):
     _parity(fr, N, Q, k, seed=N + Q, force_path=force)
+
+
+@pytest.mark.parametrize("epi_warps", [8, 16])
+@pytest.mark.parametrize("N,Q,k,d", [(400000, 300, 500, 256), (250000, 1000, 100, 128), (999999, 257, 500, 64)])
+def test_two_query_block_filter_scan_both_epilogue_layouts(fr, N, Q, k, d, epi_warps):
+    """Batches above 128 queries run the MQ = 2 filter scan; its 8-warp (one candidate segment per corpus
+    split) and 16-warp (one per 64-column half) epilogues must both give the oracle's answer."""
+    _parity(fr, N, Q, k, d=d, seed=N + Q, epi_warps=epi_warps)
 
 
 def test_ingest_normalises_like_faiss_and_never_mutates_input(fr):
