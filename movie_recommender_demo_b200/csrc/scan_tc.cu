@@ -390,6 +390,10 @@ void plan_scan(int Q, int tile_count, int num_sms, int* MQ, int* QG, int* splits
     // unit granularity: ceil/floor imbalance of tiles per split
     const double per = (double)tile_count / s;
     eff *= per / (double)ceil_div(tile_count, s);
+    // fixed cost per unit (query-block reload + pipeline fill/drain), about 1.5 tile times: irrelevant for
+    // the full scan (hundreds of tiles per unit), decisive for the short sampling pass, where 4 waves of
+    // 7-tile units took 95 us at Q=4096 against ~55 us for one wave of 28-tile units
+    eff *= per / (per + 1.5);
     if (eff > best_eff + 1e-9) { best_eff = eff; best_s = s; }
   }
   *MQ = mq;
