@@ -115,7 +115,8 @@ int b2r_index_set_label_base(b2r_index* h, int64_t base);
  * pq_scan_path = 0 (default) picks the query-major ADC scan when pq_m is 8/16/32, 1 forces the older
  * one-CTA-per-(query,list) kernel (tests compare the two); epi_warps = 16 (default) | 8 epilogue warps of
  * the flat filter scan for batches above 128 queries (16: one candidate segment per 64-column half of a
- * corpus tile, 8-9 % faster; same answers); force_path / dense_budget / profile /
+ * corpus tile, 8-9 % faster; same answers); walk = 1 (default) | 0: the filter epilogue's append walk visits
+ * only the 3-element sub-groups whose maximum passed the threshold, or all 8 scores of the group; force_path / dense_budget / profile /
  * ivf_debug are test and measurement hooks (see csrc/index.cu). */
 int b2r_index_set_param(b2r_index* h, const char* name, double value);
 double b2r_index_get_param(const b2r_index* h, const char* name);

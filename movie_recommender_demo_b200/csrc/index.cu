@@ -244,7 +244,7 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
   if (tau_in || !pl.dense) {
     const bool prof = h->profile && h->prof_used + 2 <= h->prof_ev.size();
     if (prof) cudaEventRecord(h->prof_ev[h->prof_used], stream);
-    if ((rc = launch_scan(SCAN_FILTER, MQ, tmQ, h->tmX, sp, h->num_sms, stream, epi_warps))) return rc;
+    if ((rc = launch_scan(SCAN_FILTER, MQ, tmQ, h->tmX, sp, h->num_sms, stream, epi_warps, h->walk))) return rc;
     if (prof) {
       cudaEventRecord(h->prof_ev[h->prof_used + 1], stream);
       h->prof_used += 2;
@@ -523,6 +523,7 @@ int b2r_index_set_param(b2r_index* h, const char* name, double value) {
     if (value != 8 && value != 16) return fail(B2R_EINVAL, "epi_warps must be 8 or 16");
     h->epi_warps = (int)value;
   }
+  else if (n == "walk") h->walk = value != 0;
   else if (n == "rescore") h->rescore = value != 0;
   else if (n == "force_path") h->force_path = (int)value;
   else if (n == "dense_budget") h->dense_budget = (int64_t)value;
@@ -553,6 +554,7 @@ double b2r_index_get_param(const b2r_index* h, const char* name) {
   if (n == "cand_factor") return h->cand_factor;
   if (n == "cand_cap") return h->cand_cap;
   if (n == "epi_warps") return h->epi_warps;
+  if (n == "walk") return h->walk;
   if (n == "rescore") return h->rescore;
   if (n == "force_path") return h->force_path;
   if (n == "dense_budget") return (double)h->dense_budget;

@@ -85,7 +85,7 @@ int make_tmap_bf16_rows(CUtensorMap* out, const void* base, int64_t rows, int d)
 // epi_warps: 8, or 16 for the (MQ = 2, FILTER) variant with one candidate segment per 64-column half
 // (p.nseg must then be 2 * splits, as for MQ = 1)
 int launch_scan(int mode, int MQ, const CUtensorMap& tmQ, const CUtensorMap& tmX,
-                const ScanParams& p, int num_sms, cudaStream_t stream, int epi_warps = 8);
+                const ScanParams& p, int num_sms, cudaStream_t stream, int epi_warps = 8, int walk = 0);
 // picks (MQ, splits) for a (Q, tiles) problem
 void plan_scan(int Q, int tile_count, int num_sms, int* MQ, int* QG, int* splits);
 
@@ -160,6 +160,7 @@ struct b2r_index {
   int scan_dtype_req = -1;  // -1 auto (fp16 while every add was normalised), 0 bf16, 1 fp16
   int scan_fp16 = -1;       // current format of x16 (-1: nothing stored yet)
   double cand_factor_fp16 = 2.5;
+  int walk = 1;                  // FILTER hit walk: 1 = only the passing 3-element sub-groups (2-5 % faster), 0 = all 8
   int epi_warps = 16;            // epilogue warps of the MQ = 2 filter scan (8 | 16); 16 measured 8-9 % faster
   double cand_factor = 4.0;
   int cand_cap = 4096;

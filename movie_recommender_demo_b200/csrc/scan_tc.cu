@@ -45,7 +45,7 @@ struct ScanCfg {
 
 constexpr int kEpiWarp0 = 4;
 
-template <int MODE>
+template <int MODE, int WALK>
 __device__ __forceinline__ void epi_chunk(const ScanParams& p, const uint32_t (&r)[32], int q,
                                           float tau, int64_t row0, int rows_valid, int gidx,
                                           uint2* seg, int& cnt) {
@@ -91,21 +91,37 @@ __device__ __forceinline__ void epi_chunk(const ScanParams& p, const uint32_t (&
     for (int s = 0; s < 32; s += 8) {
       const float a = fmax3(__uint_as_float(r[s]), __uint_as_float(r[s + 1]), __uint_as_float(r[s + 2]));
       const float b = fmax3(__uint_as_float(r[s + 3]), __uint_as_float(r[s + 4]), __uint_as_float(r[s + 5]));
-      const float m = fmax3(a, b, fmaxf(__uint_as_float(r[s + 6]), __uint_as_float(r[s + 7])));
+      const float c = fmaxf(__uint_as_float(r[s + 6]), __uint_as_float(r[s + 7]));
+      const float m = fmax3(a, b, c);
       if (m >= tau) {
+        if (WALK == 0) {
 #pragma unroll
-        for (int i = s; i < s + 8; ++i) {
-          if (__uint_as_float(r[i]) >= tau && i < rows_valid) {
-            if (cnt < p.cap_seg) seg[cnt] = make_uint2(r[i], (uint32_t)(row0 + i));
-            ++cnt;
+          for (int i = s; i < s + 8; ++i) {
+            if (__uint_as_float(r[i]) >= tau && i < rows_valid) {
+              if (cnt < p.cap_seg) seg[cnt] = make_uint2(r[i], (uint32_t)(row0 + i));
+              ++cnt;
+            }
           }
+        } else {
+          // walk only the sub-group(s) whose maximum passed (row order is preserved: a, b, c)
+          auto take = [&](int i) {
+            if (__uint_as_float(r[i]) >= tau) {
+              if (i < rows_valid) {
+                if (cnt < p.cap_seg) seg[cnt] = make_uint2(r[i], (uint32_t)(row0 + i));
+                ++cnt;
+              }
+            }
+          };
+          if (a >= tau) { take(s); take(s + 1); take(s + 2); }
+          if (b >= tau) { take(s + 3); take(s + 4); take(s + 5); }
+          if (c >= tau) { take(s + 6); take(s + 7); }
         }
       }
     }
   }
 }
 
-template <int MQ, int MODE, int EW>
+template <int MQ, int MODE, int EW, int WALK>
 __global__ void __launch_bounds__(128 + 32 * EW, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX,
                const ScanParams p) {
@@ -287,7 +303,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               const int64_t row0 = tile_row0 + col_begin + c * 32;
               const int64_t rv = p.N - row0;
               const int rows_valid = rv >= 32 ? 32 : (rv < 0 ? 0 : (int)rv);
-              epi_chunk<MODE>(p, r0, q, tau, row0, rows_valid, j * 4 + (col_begin >> 5) + c, seg, cnt);
+              epi_chunk<MODE, WALK>(p, r0, q, tau, row0, rows_valid, j * 4 + (col_begin >> 5) + c, seg, cnt);
             }
             tmem_ld_wait_dep(r1);
             if (c + 2 < NCH) {
@@ -302,7 +318,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               const int64_t row0 = tile_row0 + col_begin + (c + 1) * 32;
               const int64_t rv = p.N - row0;
               const int rows_valid = rv >= 32 ? 32 : (rv < 0 ? 0 : (int)rv);
-              epi_chunk<MODE>(p, r1, q, tau, row0, rows_valid, j * 4 + (col_begin >> 5) + c + 1, seg, cnt);
+              epi_chunk<MODE, WALK>(p, r1, q, tau, row0, rows_valid, j * 4 + (col_begin >> 5) + c + 1, seg, cnt);
             }
           }
         } else {
@@ -340,10 +356,10 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int MQ, int MODE, int EW = 8>
+template <int MQ, int MODE, int EW = 8, int WALK = 0>
 int launch_one(const CUtensorMap& tmQ, const CUtensorMap& tmX, const ScanParams& p, int grid,
                cudaStream_t stream) {
-  auto kern = scan_tc_kernel<MQ, MODE, EW>;
+  auto kern = scan_tc_kernel<MQ, MODE, EW, WALK>;
   static bool configured[64] = {};  // per instantiation, per device
   int dev = 0;
   B2R_CUDA(cudaGetDevice(&dev));
@@ -402,14 +418,16 @@ void plan_scan(int Q, int tile_count, int num_sms, int* MQ, int* QG, int* splits
 }
 
 int launch_scan(int mode, int MQ, const CUtensorMap& tmQ, const CUtensorMap& tmX,
-                const ScanParams& p, int num_sms, cudaStream_t stream, int epi_warps) {
+                const ScanParams& p, int num_sms, cudaStream_t stream, int epi_warps, int walk) {
   if (p.d % kKChunk != 0 || p.d < kKChunk || p.d > 256)
     return fail(B2R_EINVAL, "scan: d must be a multiple of 64 in [64,256]");
   if (p.tile_count <= 0 || p.Q <= 0) return B2R_OK;
   const int64_t units = (int64_t)p.splits * p.QG;
   const int grid = (int)(units < num_sms ? units : num_sms);
   if (MQ == 2 && mode == SCAN_FILTER && epi_warps == 16)
-    return launch_one<2, SCAN_FILTER, 16>(tmQ, tmX, p, grid, stream);
+    return walk ? launch_one<2, SCAN_FILTER, 16, 1>(tmQ, tmX, p, grid, stream)
+                : launch_one<2, SCAN_FILTER, 16, 0>(tmQ, tmX, p, grid, stream);
+  if (MQ == 1 && mode == SCAN_FILTER && walk) return launch_one<1, SCAN_FILTER, 8, 1>(tmQ, tmX, p, grid, stream);
 #define B2R_SCAN_CASE(MQ_, MODE_)                                             \
   if (MQ == MQ_ && mode == MODE_) return launch_one<MQ_, MODE_>(tmQ, tmX, p, grid, stream);
   B2R_SCAN_CASE(1, SCAN_DUMP)

@@ -23,7 +23,7 @@ def _bf16(a):
     return torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).to(torch.float32).numpy()
 
 
-def _parity(fr, N, Q, k, d=256, seed=0, force_path=0, unit=False, epi_warps=0):
+def _parity(fr, N, Q, k, d=256, seed=0, force_path=0, unit=False, epi_warps=0, walk=None):
     from oracle.compare import compare_topk
     from oracle.flat import OracleFAISSIndex
     rng = np.random.default_rng(seed)
@@ -34,6 +34,8 @@ def _parity(fr, N, Q, k, d=256, seed=0, force_path=0, unit=False, epi_warps=0):
         g.index.set_param("force_path", force_path)
     if epi_warps:
         g.index.set_param("epi_warps", epi_warps)
+    if walk is not None:
+        g.index.set_param("walk", walk)
     g.add(x)
     o = OracleFAISSIndex(d, 'Flat')
     o.add(x)
@@ -166,6 +168,14 @@ def test_two_query_block_filter_scan_both_epilogue_layouts(fr, N, Q, k, d, epi_w
     """Batches above 128 queries run the MQ = 2 filter scan; its 8-warp (one candidate segment per corpus
     split) and 16-warp (one per 64-column half) epilogues must both give the oracle's answer."""
     _parity(fr, N, Q, k, d=d, seed=N + Q, epi_warps=epi_warps)
+
+
+@pytest.mark.parametrize("walk", [0, 1])
+@pytest.mark.parametrize("N,Q,k", [(500000, 300, 500), (300000, 8, 100), (1000000, 128, 500)])
+def test_filter_hit_walk_variants(fr, N, Q, k, walk):
+    """The append walk of the filter epilogue (all 8 scores of a passing group, or only its passing
+    3-element sub-groups) is an implementation detail: both must give the oracle's answer."""
+    _parity(fr, N, Q, k, seed=N + Q + 1, walk=walk)
 
 
 def test_ingest_normalises_like_faiss_and_never_mutates_input(fr):

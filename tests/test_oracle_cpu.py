@@ -185,3 +185,29 @@ def test_oracle_hnsw_stand_in_is_exact_l2():
     brute = ((q[:, None, :] / np.linalg.norm(q, axis=1)[:, None, None]
               - (x / np.linalg.norm(x, axis=1, keepdims=True))[None]) ** 2).sum(-1)
     assert np.array_equal(np.argsort(brute, axis=1, kind="stable")[:, :50], ih[:, :50])
+
+
+def test_flat_oracles_agree_with_an_independent_bruteforce():
+    """faiss is not installable here (the retrieval oracle is unpinned against it), so at least check the
+    restatement against an independent third-party exact search: scikit-learn's brute-force
+    NearestNeighbors.  On L2-normalised rows cosine distance = 1 - <q, x> (Flat IP ranking) and squared
+    euclidean distance is what the 'HNSW' stand-in's oracle reports."""
+    from sklearn.neighbors import NearestNeighbors
+    from oracle.flat import OracleFAISSIndex, normalize_L2
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((3000, 48)).astype(np.float32)
+    q = rng.standard_normal((17, 48)).astype(np.float32)
+    k = 120
+    flat, l2 = OracleFAISSIndex(48, 'Flat'), OracleFAISSIndex(48, 'HNSW')
+    flat.add(x), l2.add(x)
+    ids_ip, d_ip = flat.search(q, k=k)
+    ids_l2, d_l2 = l2.search(q, k=k)
+    xn, qn = normalize_L2(x.copy()), normalize_L2(q.copy())
+    nn = NearestNeighbors(n_neighbors=k, algorithm="brute", metric="cosine").fit(xn.astype(np.float64))
+    dist, idx = nn.kneighbors(qn.astype(np.float64))
+    assert (idx == ids_ip).mean() > 0.999          # identical up to fp32-vs-fp64 near-ties
+    assert np.allclose(1.0 - dist, d_ip, atol=2e-6)
+    nn = NearestNeighbors(n_neighbors=k, algorithm="brute", metric="sqeuclidean").fit(xn.astype(np.float64))
+    dist, idx = nn.kneighbors(qn.astype(np.float64))
+    assert (idx == ids_l2).mean() > 0.999
+    assert np.allclose(dist, d_l2, atol=4e-6)
