@@ -211,3 +211,23 @@ def test_flat_oracles_agree_with_an_independent_bruteforce():
     dist, idx = nn.kneighbors(qn.astype(np.float64))
     assert (idx == ids_l2).mean() > 0.999
     assert np.allclose(dist, d_l2, atol=4e-6)
+
+
+def test_oracle_stage1_matches_the_reference_tower_golden():
+    """End-to-end Stage 1 on the CPU oracle (oracle towers -> oracle Flat wrapper) vs tests/golden/stage1_cfg1.npz,
+    whose embeddings came from the reference's own two_tower_model.py (make_stage1_golden.py)."""
+    from oracle.compare import compare_topk
+    from oracle.flat import OracleFAISSIndex
+    fx = np.load(GOLDEN / "stage1_cfg1.npz")
+    cfg = CONFIGS["cfg1"]
+    state = make_state(cfg, int(fx["state_seed"]))
+    _, _, acat = make_inputs(cfg, int(fx["ad_seed"]), int(fx["n_ads"]))
+    ucat, unum, _ = make_inputs(cfg, int(fx["user_seed"]), int(fx["n_users"]))
+    u = otowers.tower_forward(state, "user_tower", ucat, unum)
+    np.testing.assert_allclose(u, fx["user_out"], rtol=0, atol=5e-6)
+    index = OracleFAISSIndex(cfg["output_dim"], 'Flat')
+    index.add(otowers.tower_forward(state, "ad_tower", acat), [10 * i + 3 for i in range(int(fx["n_ads"]))])
+    k = int(fx["k"])
+    ids, dist = index.search(u, k=k)
+    # the two tower implementations differ by ~1e-6 per component: order may differ inside 1e-5 score gaps only
+    compare_topk(ids, dist, fx["ids"], fx["dist"], k, gap_tol=1e-5, score_rtol=0, score_atol=1e-5)
