@@ -393,6 +393,9 @@ def run_b200(args):
                 + " operands / fp32 accumulate tcgen05 scan (unit-norm rows), exact fp32 rescore of the final candidates",
                 "l2_policy": "no flush: corpus (bf16 scan copy + fp32 master) is larger than the 126 MB L2",
                 "corpus_build_s": round(t_build, 2),
+                "scaling_note": ("the N=1 line is BASELINE configs[1] (1M-row corpus on one GPU); N>1 lines are "
+                                 "configs[4] (the 100M-row corpus row-sharded over N GPUs, strong scaling): compare "
+                                 "the N>1 lines among themselves, or scan_throughput (query*rows/s) across all N"),
                 "launch": ("CUDA-graph replay of the search's launch sequence (batch <= 256)" if world == 1 and Q <= 256
                            else "eager stream launches"),
             },
