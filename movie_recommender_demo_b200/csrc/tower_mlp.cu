@@ -19,7 +19,12 @@
 //   gemm_bias_act<BN>   128 x BN output tile per CTA step, K streamed in 64-element chunks
 //                       through a 4-slot TMA/mbarrier ring; TMEM double-buffered (2 x BN cols);
 //                       epilogue thread == output row, so the L2 norm of the last layer is a
-//                       per-thread reduction over its TMEM lane.
+//                       per-thread reduction over its TMEM lane.  Output rows leave through a
+//                       per-warp shared-memory transpose: a thread owns a ROW, so storing from
+//                       registers sent 32 half-used sectors per instruction (ncu: 32 sectors per
+//                       request, 2x the payload in write traffic, the LSU store path at ~2.5 cycles
+//                       per sector was the bound of all three layers); after the transpose 8 lanes
+//                       write 128 contiguous bytes of one row (4 full lines per instruction).
 #include <cuda_fp16.h>
 #include <string.h>
 
@@ -113,7 +118,8 @@ struct GemmCfg {
   static constexpr int SLOT_B = BN * 128;
   static constexpr int SLOT = SLOT_A + SLOT_B;
   static constexpr int NBARS = 2 * kGemmSlots + 4;
-  static constexpr int SMEM = 1024 + kGemmSlots * SLOT + NBARS * 8 + 64 + BN * 4;
+  static constexpr int STAGE = 4 * 4096;   // per epilogue warp: 32 rows x 128 B transpose buffer
+  static constexpr int SMEM = 1024 + kGemmSlots * SLOT + NBARS * 8 + 64 + BN * 4 + STAGE;
 };
 
 struct GemmParams {
@@ -143,6 +149,8 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   auto bar_tempty = [&](int i) { return bar0 + 8u * (2 * NS + 2 + i); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + NS * Cfg::SLOT + Cfg::NBARS * 8);
   float* bias_s = reinterpret_cast<float*>(smem + NS * Cfg::SLOT + Cfg::NBARS * 8 + 64);
+  // transpose buffers behind the bias slice; 16-byte aligned (SLOT, NBARS*8 + 64 and BN*4 are multiples of 16)
+  const uint32_t stage0 = base + NS * Cfg::SLOT + Cfg::NBARS * 8 + 64 + BN * 4;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 1 && lane == 0) {
@@ -220,7 +228,6 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint32_t tph = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int mt = u / n_tiles, nt = u % n_tiles;
-      const int64_t row = (int64_t)mt * 128 + quarter * 32 + lane;
       const int n0 = nt * BN;
       // stage this tile's bias slice (all four epilogue warps, named barrier 1)
       asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
@@ -230,8 +237,14 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tb * BN);
       uint32_t r[32];
+      // transpose buffer of this warp: row l at stg + l*128, its 16-byte piece j stored at slot j ^ (l & 7)
+      // (a quarter-warp of 128-bit accesses then covers all 32 banks once, on the write and on the read side)
+      const uint32_t stg = stage0 + (uint32_t)quarter * 4096u;
+      const uint32_t st_row = stg + (uint32_t)lane * 128u;
+      const int rd_r = lane >> 3, rd_j = lane & 7;    // read side: lane -> (row within a group of 4, piece)
+      const int64_t row_base = (int64_t)mt * 128 + quarter * 32;
       if (p.mode == 0) {
-        __half* orow = reinterpret_cast<__half*>(p.out) + row * p.ldo + n0;
+        __half* obase = reinterpret_cast<__half*>(p.out) + n0;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           tmem_ld_32x32(taddr + c * 32, r);
@@ -243,10 +256,22 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const float b = fmaxf(__uint_as_float(r[i + 1]) + bias_s[c * 32 + i + 1], 0.f);
             pk[i >> 1] = pack_h2(a, b);
           }
-          if (row < p.M) {
+          // 32 fp16 = 64 B per row per chunk: pieces (c & 1) * 4 .. + 3 of the 128-byte slab row
 #pragma unroll
-            for (int i = 0; i < 16; i += 4)
-              *reinterpret_cast<uint4*>(orow + c * 32 + i * 2) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t piece = (uint32_t)(((c & 1) * 4 + j) ^ (lane & 7));
+            st_shared_v4(st_row + piece * 16u, pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+          if (c & 1) {   // a 64-column slab is complete: 8 lanes per row, 4 rows per store instruction
+            __syncwarp();
+#pragma unroll
+            for (int pass = 0; pass < 8; ++pass) {
+              const int rr = pass * 4 + rd_r;
+              const uint4 v = ld_shared_v4(stg + (uint32_t)rr * 128u + (uint32_t)((rd_j ^ (rr & 7)) * 16));
+              const int64_t grow = row_base + rr;
+              if (grow < p.M) *reinterpret_cast<uint4*>(obase + grow * p.ldo + (c >> 1) * 64 + rd_j * 8) = v;
+            }
+            __syncwarp();
           }
         }
       } else {
@@ -262,28 +287,39 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
         }
         const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(||x||, eps)
-        float* orow = reinterpret_cast<float*>(p.out) + row * p.ldo + n0;
+        float* obase = reinterpret_cast<float*>(p.out) + n0;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait_dep(r);
-          if (row < p.M) {
+          // 32 fp32 = 128 B per row per chunk = one slab row
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const int col = n0 + c * 32 + i;
-              float4 o;
-              o.x = (__uint_as_float(r[i]) + bias_s[c * 32 + i]) * inv;
-              o.y = (__uint_as_float(r[i + 1]) + bias_s[c * 32 + i + 1]) * inv;
-              o.z = (__uint_as_float(r[i + 2]) + bias_s[c * 32 + i + 2]) * inv;
-              o.w = (__uint_as_float(r[i + 3]) + bias_s[c * 32 + i + 3]) * inv;
-              if (col + 4 <= p.n_store) *reinterpret_cast<float4*>(orow + c * 32 + i) = o;
+          for (int j = 0; j < 8; ++j) {
+            const int i = 4 * j;
+            st_shared_v4(st_row + (uint32_t)((j ^ (lane & 7)) * 16),
+                         __float_as_uint((__uint_as_float(r[i]) + bias_s[c * 32 + i]) * inv),
+                         __float_as_uint((__uint_as_float(r[i + 1]) + bias_s[c * 32 + i + 1]) * inv),
+                         __float_as_uint((__uint_as_float(r[i + 2]) + bias_s[c * 32 + i + 2]) * inv),
+                         __float_as_uint((__uint_as_float(r[i + 3]) + bias_s[c * 32 + i + 3]) * inv));
+          }
+          __syncwarp();
+#pragma unroll
+          for (int pass = 0; pass < 8; ++pass) {
+            const int rr = pass * 4 + rd_r;
+            const uint4 v = ld_shared_v4(stg + (uint32_t)rr * 128u + (uint32_t)((rd_j ^ (rr & 7)) * 16));
+            const int64_t grow = row_base + rr;
+            if (grow < p.M) {
+              const int col = n0 + c * 32 + rd_j * 4;
+              float* o = obase + grow * p.ldo + c * 32 + rd_j * 4;
+              if (col + 4 <= p.n_store) *reinterpret_cast<uint4*>(o) = v;
               else {
-                if (col < p.n_store) orow[c * 32 + i] = o.x;
-                if (col + 1 < p.n_store) orow[c * 32 + i + 1] = o.y;
-                if (col + 2 < p.n_store) orow[c * 32 + i + 2] = o.z;
+                if (col < p.n_store) o[0] = __uint_as_float(v.x);
+                if (col + 1 < p.n_store) o[1] = __uint_as_float(v.y);
+                if (col + 2 < p.n_store) o[2] = __uint_as_float(v.z);
               }
             }
           }
+          __syncwarp();
         }
       }
       tc_fence_before_sync();
