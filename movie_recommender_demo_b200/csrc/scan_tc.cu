@@ -47,7 +47,7 @@ constexpr int kEpiWarp0 = 4;
 
 template <int MODE, int WALK>
 __device__ __forceinline__ void epi_chunk(const ScanParams& p, const uint32_t (&r)[32], int q,
-                                          float tau, int64_t row0, int rows_valid, int gidx,
+                                          float tau, int64_t row0, int rows_valid, float& gmax_out,
                                           uint2* seg, int& cnt) {
   // r[i] = score(query q, corpus row row0 + i); rows_valid = number of i with row0+i < N (<=32)
   if (MODE == SCAN_DUMP) {
@@ -82,7 +82,7 @@ __device__ __forceinline__ void epi_chunk(const ScanParams& p, const uint32_t (&
       for (int i = 0; i < 32; ++i)
         if (i < rows_valid) m = fmaxf(m, __uint_as_float(r[i]));
     }
-    p.gmax[(size_t)q * p.gstride + gidx] = m;
+    gmax_out = m;   // stored by the caller, several chunks per store instruction
   } else {  // SCAN_FILTER
     // per-lane test of 8 scores at a time (3-input max tree): ~0.6 instructions per score on the
     // common path.  A lane with a hit walks its 8 values and appends to ITS query's private
@@ -293,6 +293,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                                  (uint32_t)((tb * MQ + h) * 128 + col_begin);
           uint32_t r0[32], r1[32];
+          // GMAX: a lane owns a QUERY, so its group maxima go to its own row of p.gmax - 32 different
+          // sectors per store instruction.  Keep the tile's maxima in registers and store them 8 or 16
+          // bytes at a time (4x fewer store sectors than one 4-byte store per chunk).
+          float gm0 = 0.f, gm1 = 0.f, gm_prev0 = 0.f, gm_prev1 = 0.f;
           tmem_ld_32x32(taddr, r0);
 #pragma unroll 1
           for (int c = 0; c < NCH; c += 2) {
@@ -303,7 +307,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               const int64_t row0 = tile_row0 + col_begin + c * 32;
               const int64_t rv = p.N - row0;
               const int rows_valid = rv >= 32 ? 32 : (rv < 0 ? 0 : (int)rv);
-              epi_chunk<MODE, WALK>(p, r0, q, tau, row0, rows_valid, j * 4 + (col_begin >> 5) + c, seg, cnt);
+              epi_chunk<MODE, WALK>(p, r0, q, tau, row0, rows_valid, gm0, seg, cnt);
             }
             tmem_ld_wait_dep(r1);
             if (c + 2 < NCH) {
@@ -318,7 +322,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               const int64_t row0 = tile_row0 + col_begin + (c + 1) * 32;
               const int64_t rv = p.N - row0;
               const int rows_valid = rv >= 32 ? 32 : (rv < 0 ? 0 : (int)rv);
-              epi_chunk<MODE, WALK>(p, r1, q, tau, row0, rows_valid, j * 4 + (col_begin >> 5) + c + 1, seg, cnt);
+              epi_chunk<MODE, WALK>(p, r1, q, tau, row0, rows_valid, gm1, seg, cnt);
+            }
+            if (MODE == SCAN_GMAX) {
+              float* dst = p.gmax + (size_t)q * p.gstride + j * 4 + (col_begin >> 5);   // 16-byte aligned (gstride % 4 == 0)
+              if (NCH == 2) {
+                *reinterpret_cast<float2*>(dst) = make_float2(gm0, gm1);
+              } else if (c == 0) {
+                gm_prev0 = gm0;
+                gm_prev1 = gm1;
+              } else {
+                *reinterpret_cast<float4*>(dst) = make_float4(gm_prev0, gm_prev1, gm0, gm1);
+              }
             }
           }
         } else {
