@@ -205,12 +205,29 @@ typedef struct b2r_tower_weights {
 /* Replaces UserTower/AdTower construction + load_state_dict + eval(). */
 int b2r_tower_create(b2r_tower** out, const b2r_tower_weights* w, int device);
 int b2r_tower_destroy(b2r_tower* t);
+/* Workspace bytes b2r_tower_forward needs for a batch of B (0 when the fused kernel serves this tower:
+ * it keeps every intermediate activation on the SM). */
 size_t b2r_tower_workspace(const b2r_tower* t, int64_t B);
 
+/* Tunables: operand_dtype = 0 fp16 (default: 8x smaller rounding error than bf16, same tensor rate) | 1 bf16
+ * (fp32 range; chosen automatically at create time when a BN-folded weight exceeds the fp16 range, and by the
+ * caller when a forward reports B2R_TOWER_SATURATED); force_path = 0 auto | 1 layer-by-layer kernels (gather +
+ * 3 GEMM launches, any widths) | 2 fused kernel (hidden widths <= 512 / 256, out_dim <= 256 and % 4 == 0).
+ * get_param also answers "fused" (1 when the next forward takes the fused kernel). */
+int b2r_tower_set_param(b2r_tower* t, const char* name, double value);
+double b2r_tower_get_param(const b2r_tower* t, const char* name);
+
+/* bits OR-ed into *err_flag by b2r_tower_forward (the flag is never cleared by the library) */
+#define B2R_TOWER_BAD_INDEX 1   /* a categorical id was outside [0, card): torch raises IndexError there */
+#define B2R_TOWER_SATURATED 2   /* an fp16 operand (input or hidden activation) exceeded +-65504 and was clipped:
+                                   the output of this call is not trustworthy, rerun with operand_dtype = 1 */
+
 /* Replaces UserTower.forward / AdTower.forward (two_tower_model.py:98-121,
- * :167-184) in eval mode: gather+concat -> 3 GEMMs (bf16 operands, fp32
- * accumulate) with bias/ReLU -> F.normalize(p=2, eps=1e-12).
- * cat int64 [B,F]; num fp32 [B,num_numerical] or NULL; out fp32 [B,out_dim]. */
+ * :167-184) in eval mode: gather+concat -> 3 GEMMs (16-bit operands, fp32
+ * accumulate) with bias/ReLU -> F.normalize(p=2, eps=1e-12); one fused kernel
+ * when the shape allows (see b2r_tower_set_param).
+ * cat int64 [B,F]; num fp32 [B,num_numerical] or NULL; out fp32 [B,out_dim];
+ * err_flag int32 device (B2R_TOWER_* bits are OR-ed in) or NULL. */
 int b2r_tower_forward(b2r_tower* t, const int64_t* cat, const float* num, int64_t B, float* out,
                       int32_t* err_flag, void* workspace, size_t ws_bytes, void* stream);
 

@@ -19,6 +19,7 @@ OK, EINVAL, ECUDA, ENOMEM, ESTATE, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 KIND_FLAT, KIND_IVF_FLAT, KIND_IVF_PQ = 0, 1, 2
 METRIC_IP, METRIC_L2 = 0, 1
 ST_TOO_FEW, ST_NEED_LOWER_TAU, ST_CAND_OVERFLOW, ST_RESCORE_OVERFLOW = 1, 2, 4, 8
+TOWER_BAD_INDEX, TOWER_SATURATED = 1, 2
 
 _lib = None
 
@@ -90,6 +91,8 @@ def load():
         "b2r_tower_create": (i32, [C.POINTER(vp), C.POINTER(TowerWeights), i32]),
         "b2r_tower_destroy": (i32, [vp]),
         "b2r_tower_workspace": (sz, [vp, i64]),
+        "b2r_tower_set_param": (i32, [vp, C.c_char_p, dbl]),
+        "b2r_tower_get_param": (dbl, [vp, C.c_char_p]),
         "b2r_tower_forward": (i32, [vp, vp, vp, i64, vp, vp, vp, sz, vp]),
         "b2r_debug_scores_tc": (i32, [vp, i32, vp, i32, vp, vp, sz, vp]),
         "b2r_debug_scores_simt": (i32, [vp, i32, vp, i32, vp, vp]),

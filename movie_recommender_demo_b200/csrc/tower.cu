@@ -53,7 +53,7 @@ gather_concat_kernel(const float* const* __restrict__ tables, const int64_t* __r
         const int w = w0 + u * 32 + lane;
         if (w < W) *reinterpret_cast<float4*>(out + b * ld + (int64_t)w * 4) = v[u];
       }
-      if (bad && err_flag) *err_flag = 1;
+      if (bad && err_flag) atomicOr(err_flag, 1);   // B2R_TOWER_BAD_INDEX
     }
   }
 }

@@ -26,12 +26,13 @@
 //                       per sector was the bound of all three layers); after the transpose 8 lanes
 //                       write 128 contiguous bytes of one row (4 full lines per instruction).
 #include <cuda_fp16.h>
+#include <math.h>
 #include <string.h>
 
 #include <vector>
 
-#include "internal.h"
 #include "ptx.cuh"
+#include "tower_internal.h"
 
 namespace b2r {
 namespace {
@@ -46,25 +47,36 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
                : "l"(p));
   return v;
 }
-// fp32 pair -> packed fp16x2, round-to-nearest, saturating to +-65504 instead of inf
+// fp32 pair -> packed 16-bit pair.  fp16: round-to-nearest, saturating to +-65504 instead of inf (the callers
+// track max |v| and raise kTowerErrSaturate, so a clipped result is never silent); bf16: fp32 range.
+template <bool BF16>
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   uint32_t r;
-  asm("{\n\t.reg .b16 l, h;\n\t"
-      "cvt.rn.satfinite.f16.f32 l, %1;\n\t"
-      "cvt.rn.satfinite.f16.f32 h, %2;\n\t"
-      "mov.b32 %0, {l, h};\n\t}"
-      : "=r"(r)
-      : "f"(lo), "f"(hi));
+  if (BF16) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  } else {
+    asm("{\n\t.reg .b16 l, h;\n\t"
+        "cvt.rn.satfinite.f16.f32 l, %1;\n\t"
+        "cvt.rn.satfinite.f16.f32 h, %2;\n\t"
+        "mov.b32 %0, {l, h};\n\t}"
+        : "=r"(r)
+        : "f"(lo), "f"(hi));
+  }
   return r;
 }
+template <bool BF16>
 __device__ __forceinline__ uint2 pack_h4(float4 v) {
   uint2 pk;
-  pk.x = pack_h2(v.x, v.y);
-  pk.y = pack_h2(v.z, v.w);
+  pk.x = pack_h2<BF16>(v.x, v.y);
+  pk.y = pack_h2<BF16>(v.z, v.w);
   return pk;
+}
+__device__ __forceinline__ float absmax4(float4 v) {
+  return fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
 }
 
 // out: fp16 [B, K1p]; columns [0, F*E) embeddings, [F*E, F*E+nnum) numericals, rest zero.
+template <bool BF16>
 __global__ void __launch_bounds__(kGatherWarps * 32)
 tower_gather_f16_kernel(const float* const* __restrict__ tables, const int64_t* __restrict__ cards,
                          int F, int E4, const int64_t* __restrict__ idx, const float* __restrict__ num,
@@ -75,6 +87,8 @@ tower_gather_f16_kernel(const float* const* __restrict__ tables, const int64_t* 
   const int64_t warp0 = (int64_t)blockIdx.x * kGatherWarps + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kGatherWarps;
   const int tail0 = W * 4;  // first non-embedding column
+  float amax = 0.f;
+  bool any_bad = false;
   for (int64_t b = warp0; b < B; b += nwarps) {
     __half* orow = out + b * K1p;
     for (int w0 = 0; w0 < W; w0 += 128) {
@@ -96,16 +110,24 @@ tower_gather_f16_kernel(const float* const* __restrict__ tables, const int64_t* 
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int w = w0 + u * 32 + lane;
-        if (w < W) *reinterpret_cast<uint2*>(orow + (int64_t)w * 4) = pack_h4(v[u]);
+        if (w < W) {
+          if (!BF16) amax = fmaxf(amax, absmax4(v[u]));
+          *reinterpret_cast<uint2*>(orow + (int64_t)w * 4) = pack_h4<BF16>(v[u]);
+        }
       }
-      if (bad && err_flag) *err_flag = 1;
+      any_bad |= bad;
     }
     for (int c = tail0 + lane; c < K1p; c += 32) {
       const int j = c - tail0;
-      const uint32_t h2 = pack_h2(j < nnum ? num[b * nnum + j] : 0.f, 0.f);
+      const float nv = j < nnum ? num[b * nnum + j] : 0.f;
+      if (!BF16) amax = fmaxf(amax, fabsf(nv));
+      const uint32_t h2 = pack_h2<BF16>(nv, 0.f);
       orow[c] = __ushort_as_half((unsigned short)(h2 & 0xFFFFu));
     }
   }
+  int flags = any_bad ? kTowerErrIndex : 0;
+  if (!BF16 && !(amax <= 65504.f)) flags |= kTowerErrSaturate;
+  if (flags && err_flag) atomicOr(err_flag, flags);
 }
 
 // -------------------------------------------------------------------- GEMM ---
@@ -129,10 +151,11 @@ struct GemmParams {
   void* out;      // mode 0: fp16 [M, ldo]; mode 1: fp32 [M, ldo]
   int64_t ldo;
   int n_store;    // columns actually stored (mode 1: out_dim <= N)
-  int mode;       // 0: bias + ReLU -> fp16     1: bias -> L2 normalise -> fp32
+  int mode;       // 0: bias + ReLU -> 16-bit   1: bias -> L2 normalise -> fp32
+  int32_t* err_flag;  // kTowerErrSaturate when an fp16 activation clipped
 };
 
-template <int BN>
+template <int BN, bool BF16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                      const GemmParams p) {
@@ -194,7 +217,7 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   } else if (warp == 1) {
     // MMA issuer: uniform loop for the whole warp, one elected lane issues (see scan_tc.cu)
     {
-      constexpr uint32_t idesc = umma_idesc_f16_f32(128, BN);
+      constexpr uint32_t idesc = BF16 ? umma_idesc_bf16_f32(128, BN) : umma_idesc_f16_f32(128, BN);
       const uint64_t desc0 = umma_desc_kmajor_sw128(base);
       int slot = 0, tb = 0;
       uint32_t ph = 0, tph = 0;
@@ -226,6 +249,7 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int et = threadIdx.x - 128;  // 0..127
     int tb = 0;
     uint32_t tph = 0;
+    float amax = 0.f;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int mt = u / n_tiles, nt = u % n_tiles;
       const int n0 = nt * BN;
@@ -254,7 +278,8 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int i = 0; i < 32; i += 2) {
             const float a = fmaxf(__uint_as_float(r[i]) + bias_s[c * 32 + i], 0.f);
             const float b = fmaxf(__uint_as_float(r[i + 1]) + bias_s[c * 32 + i + 1], 0.f);
-            pk[i >> 1] = pack_h2(a, b);
+            if (!BF16) amax = fmaxf(amax, fmaxf(a, b));
+            pk[i >> 1] = pack_h2<BF16>(a, b);
           }
           // 32 fp16 = 64 B per row per chunk: pieces (c & 1) * 4 .. + 3 of the 128-byte slab row
 #pragma unroll
@@ -327,6 +352,7 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (lane == 0) mbar_arrive(bar_tempty(tb));
       if (++tb == 2) { tb = 0; tph ^= 1; }
     }
+    if (!BF16 && !(amax <= 65504.f) && p.err_flag) atomicOr(p.err_flag, kTowerErrSaturate);
   }
   __syncwarp();
   tc_fence_before_sync();
@@ -342,7 +368,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_tmap_f16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int box_rows) {
+int make_tmap_16_impl(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int box_rows) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* sym = nullptr;
@@ -363,10 +389,10 @@ int make_tmap_f16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t c
   return B2R_OK;
 }
 
-template <int BN>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, int num_sms,
-                cudaStream_t stream) {
-  auto kern = gemm_bias_act_kernel<BN>;
+template <int BN, bool BF16>
+int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, int num_sms,
+                  cudaStream_t stream) {
+  auto kern = gemm_bias_act_kernel<BN, BF16>;
   static bool configured[64] = {};
   int dev = 0;
   B2R_CUDA(cudaGetDevice(&dev));
@@ -380,6 +406,12 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams
   B2R_CHECK_LAUNCH("gemm_bias_act_kernel");
   return B2R_OK;
 }
+template <int BN>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, int num_sms,
+                cudaStream_t stream, bool bf16) {
+  return bf16 ? launch_gemm_t<BN, true>(tmA, tmW, p, num_sms, stream)
+              : launch_gemm_t<BN, false>(tmA, tmW, p, num_sms, stream);
+}
 
 uint16_t f32_to_f16_sat(float f) {
   if (f > 65504.f) f = 65504.f;
@@ -390,25 +422,24 @@ uint16_t f32_to_f16_sat(float f) {
   return u;
 }
 
+uint16_t f32_to_bf16(float f) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(f);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+}
+
 int pad_to(int v, int m) { return (v + m - 1) / m * m; }
 
 }  // namespace
+
+int make_tmap_f16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int box_rows) {
+  return make_tmap_16_impl(out, base, rows, cols, box_rows);
+}
+
 }  // namespace b2r
 
 using namespace b2r;
-
-struct b2r_tower {
-  int device = 0, num_sms = 148;
-  int F = 0, E = 0, nnum = 0;
-  int K1 = 0, K1p = 0;           // layer-1 fan-in and its 64-padding
-  int n[3] = {0, 0, 0};          // true fan-outs
-  int np[3] = {0, 0, 0};         // padded to a multiple of 128
-  __half* w[3] = {nullptr, nullptr, nullptr};  // [np[l], Kp[l]] fp16, zero padded
-  float* b[3] = {nullptr, nullptr, nullptr};          // [np[l]]
-  const float** tables = nullptr;  // device array [F]
-  int64_t* cards = nullptr;        // device array [F]
-  CUtensorMap tmW[3];
-};
 
 extern "C" {
 
@@ -416,6 +447,7 @@ int b2r_tower_destroy(b2r_tower* t) {
   if (!t) return B2R_OK;
   for (int l = 0; l < 3; ++l) {
     cudaFree(t->w[l]);
+    cudaFree(t->wb[l]);
     cudaFree(t->b[l]);
   }
   cudaFree((void*)t->tables);
@@ -448,27 +480,47 @@ int b2r_tower_create(b2r_tower** out, const b2r_tower_weights* w, int device) {
   t->K1p = pad_to(t->K1, 64);
   t->n[0] = w->hidden1; t->n[1] = w->hidden2; t->n[2] = w->out_dim;
   for (int l = 0; l < 3; ++l) t->np[l] = pad_to(t->n[l], 128);
+  // the fused kernel keeps H1 (128 x N1p) in 128 KB of shared memory and all accumulators in 512 TMEM columns;
+  // its TMA output stores need 16-byte aligned rows
+  t->fused_ok = t->np[0] <= 512 && t->np[1] <= 256 && t->np[2] <= 256 && (t->n[2] % 4) == 0;
+  memset(t->bias_host, 0, sizeof(t->bias_host));
   const int kin[3] = {t->K1, t->n[0], t->n[1]};
   const int kp[3] = {t->K1p, t->np[0], t->np[1]};
   const float* W[3] = {w->w1, w->w2, w->w3};
   const float* Bv[3] = {w->b1, w->b2, w->b3};
   int rc = B2R_OK;
+  float wmax = 0.f;
+  int boff = 0;
   for (int l = 0; l < 3 && rc == B2R_OK; ++l) {
-    std::vector<uint16_t> wb((size_t)t->np[l] * kp[l], 0);
+    std::vector<uint16_t> wh((size_t)t->np[l] * kp[l], 0), wbf((size_t)t->np[l] * kp[l], 0);
     std::vector<float> bb((size_t)t->np[l], 0.f);
     for (int o = 0; o < t->n[l]; ++o) {
-      for (int i = 0; i < kin[l]; ++i) wb[(size_t)o * kp[l] + i] = f32_to_f16_sat(W[l][(size_t)o * kin[l] + i]);
+      for (int i = 0; i < kin[l]; ++i) {
+        const float v = W[l][(size_t)o * kin[l] + i];
+        if (!(fabsf(v) <= wmax)) wmax = fabsf(v);   // NaN propagates into wmax
+        wh[(size_t)o * kp[l] + i] = f32_to_f16_sat(v);
+        wbf[(size_t)o * kp[l] + i] = f32_to_bf16(v);
+      }
       bb[o] = Bv[l][o];
     }
-    if (cudaMalloc(&t->w[l], wb.size() * 2) != cudaSuccess || cudaMalloc(&t->b[l], bb.size() * 4) != cudaSuccess) {
+    if (t->fused_ok) memcpy(t->bias_host + boff, bb.data(), bb.size() * 4);
+    boff += t->np[l];
+    if (cudaMalloc(&t->w[l], wh.size() * 2) != cudaSuccess || cudaMalloc(&t->wb[l], wbf.size() * 2) != cudaSuccess ||
+        cudaMalloc(&t->b[l], bb.size() * 4) != cudaSuccess) {
       rc = fail(B2R_ENOMEM, "tower_create: cudaMalloc failed");
       break;
     }
-    cudaMemcpy(t->w[l], wb.data(), wb.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(t->w[l], wh.data(), wh.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(t->wb[l], wbf.data(), wbf.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(t->b[l], bb.data(), bb.size() * 4, cudaMemcpyHostToDevice);
     const int bn = (t->np[l] % 256 == 0) ? 256 : 128;
     rc = make_tmap_f16_2d(&t->tmW[l], t->w[l], t->np[l], kp[l], bn);
+    if (!rc) rc = make_tmap_f16_2d(&t->tmWb[l], t->wb[l], t->np[l], kp[l], bn);
+    if (!rc) rc = make_tmap_f16_2d(&t->tmWf[l], t->w[l], t->np[l], kp[l], 128);
+    if (!rc) rc = make_tmap_f16_2d(&t->tmWfb[l], t->wb[l], t->np[l], kp[l], 128);
   }
+  // a BN-folded weight outside the fp16 range (tiny running_var, huge gamma): bf16 operands from the start
+  if (!(wmax <= 65504.f)) t->bf16 = 1;
   if (rc == B2R_OK) {
     if (cudaMalloc((void**)&t->tables, (size_t)t->F * 8) != cudaSuccess ||
         cudaMalloc(&t->cards, (size_t)t->F * 8) != cudaSuccess)
@@ -486,8 +538,37 @@ int b2r_tower_create(b2r_tower** out, const b2r_tower_weights* w, int device) {
   return B2R_OK;
 }
 
+int b2r_tower_set_param(b2r_tower* t, const char* name, double value) {
+  if (!t || !name) return fail(B2R_EINVAL, "tower_set_param: NULL argument");
+  const std::string n(name);
+  if (n == "operand_dtype") {         // 0 fp16 | 1 bf16
+    if (value != 0 && value != 1) return fail(B2R_EINVAL, "operand_dtype must be 0 (fp16) or 1 (bf16)");
+    t->bf16 = (int)value;
+  } else if (n == "force_path") {     // 0 auto | 1 layer-by-layer | 2 fused
+    if (value == 2 && !t->fused_ok) return fail(B2R_EUNSUPPORTED, "this tower's shape does not fit the fused kernel");
+    t->force_path = (int)value;
+  } else {
+    return fail(B2R_EINVAL, "tower_set_param: unknown parameter " + n);
+  }
+  return B2R_OK;
+}
+
+double b2r_tower_get_param(const b2r_tower* t, const char* name) {
+  if (!t || !name) return NAN;
+  const std::string n(name);
+  if (n == "operand_dtype") return t->bf16;
+  if (n == "force_path") return t->force_path;
+  if (n == "fused") return (t->force_path == 2 || (t->force_path == 0 && t->fused_ok)) ? 1 : 0;
+  return NAN;
+}
+
+static bool tower_uses_fused(const b2r_tower* t) {
+  return t->fused_ok && t->force_path != 1;
+}
+
 size_t b2r_tower_workspace(const b2r_tower* t, int64_t B) {
   if (!t || B <= 0) return 0;
+  if (tower_uses_fused(t)) return 0;     // the fused kernel keeps every intermediate on the SM
   size_t s = 0;
   s += align_up((size_t)B * t->K1p * 2, 256);
   s += align_up((size_t)B * t->np[0] * 2, 256);
@@ -502,11 +583,20 @@ int b2r_tower_forward(b2r_tower* t, const int64_t* cat, const float* num, int64_
   if (t->nnum > 0 && B > 0 && !num) return fail(B2R_EINVAL, "tower_forward: numerical features required");
   if (B == 0) return B2R_OK;
   if (B > 0x7FFFFF00ll) return fail(B2R_EUNSUPPORTED, "tower_forward: batch too large");
-  if (!workspace || ws_bytes < b2r_tower_workspace(t, B)) return fail(B2R_ENOMEM, "tower_forward: workspace too small");
   cudaStream_t stream = (cudaStream_t)stream_;
   int prev = 0;
   B2R_CUDA(cudaGetDevice(&prev));
   if (prev != t->device) B2R_CUDA(cudaSetDevice(t->device));
+  if (tower_uses_fused(t)) {
+    const int rc = launch_tower_fused(t, cat, num, B, out, err_flag, stream);
+    if (prev != t->device) cudaSetDevice(prev);
+    return rc;
+  }
+  if (!workspace || ws_bytes < b2r_tower_workspace(t, B)) {
+    if (prev != t->device) cudaSetDevice(prev);
+    return fail(B2R_ENOMEM, "tower_forward: workspace too small");
+  }
+  const bool bf = t->bf16 != 0;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   __half* a1 = reinterpret_cast<__half*>(ws);
   __half* h1 = reinterpret_cast<__half*>(ws + align_up((size_t)B * t->K1p * 2, 256));
@@ -516,8 +606,12 @@ int b2r_tower_forward(b2r_tower* t, const int64_t* cat, const float* num, int64_
     int64_t blocks = ceil_div(B, kGatherWarps);
     const int64_t maxb = (int64_t)t->num_sms * 8;
     if (blocks > maxb) blocks = maxb;
-    tower_gather_f16_kernel<<<(unsigned)blocks, kGatherWarps * 32, 0, stream>>>(
-        t->tables, t->cards, t->F, t->E / 4, cat, num, t->nnum, B, a1, t->K1p, err_flag);
+    if (bf)
+      tower_gather_f16_kernel<true><<<(unsigned)blocks, kGatherWarps * 32, 0, stream>>>(
+          t->tables, t->cards, t->F, t->E / 4, cat, num, t->nnum, B, a1, t->K1p, err_flag);
+    else
+      tower_gather_f16_kernel<false><<<(unsigned)blocks, kGatherWarps * 32, 0, stream>>>(
+          t->tables, t->cards, t->F, t->E / 4, cat, num, t->nnum, B, a1, t->K1p, err_flag);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) rc = fail(B2R_ECUDA, std::string("launch tower_gather_f16_kernel: ") + cudaGetErrorString(e));
     else count_launch();
@@ -529,6 +623,7 @@ int b2r_tower_forward(b2r_tower* t, const int64_t* cat, const float* num, int64_
     CUtensorMap tmA;
     rc = make_tmap_f16_2d(&tmA, act[l], B, kp[l], 128);
     if (rc) break;
+    const CUtensorMap& tmW = bf ? t->tmWb[l] : t->tmW[l];
     GemmParams gp;
     gp.M = B;
     gp.N = t->np[l];
@@ -538,15 +633,16 @@ int b2r_tower_forward(b2r_tower* t, const int64_t* cat, const float* num, int64_
     gp.ldo = (l == 2) ? t->n[2] : t->np[l];
     gp.n_store = (l == 2) ? t->n[2] : t->np[l];
     gp.mode = (l == 2) ? 1 : 0;
+    gp.err_flag = err_flag;
     if (l == 2 && t->np[2] > 256) { rc = fail(B2R_EUNSUPPORTED, "tower_forward: out_dim > 256"); break; }
     if (l == 2) {
       // the normalising epilogue needs the whole output row in one tile
-      if (t->np[2] == 256) rc = launch_gemm<256>(tmA, t->tmW[l], gp, t->num_sms, stream);
-      else rc = launch_gemm<128>(tmA, t->tmW[l], gp, t->num_sms, stream);
+      if (t->np[2] == 256) rc = launch_gemm<256>(tmA, tmW, gp, t->num_sms, stream, bf);
+      else rc = launch_gemm<128>(tmA, tmW, gp, t->num_sms, stream, bf);
     } else if (t->np[l] % 256 == 0) {
-      rc = launch_gemm<256>(tmA, t->tmW[l], gp, t->num_sms, stream);
+      rc = launch_gemm<256>(tmA, tmW, gp, t->num_sms, stream, bf);
     } else {
-      rc = launch_gemm<128>(tmA, t->tmW[l], gp, t->num_sms, stream);
+      rc = launch_gemm<128>(tmA, tmW, gp, t->num_sms, stream, bf);
     }
   }
   if (prev != t->device) cudaSetDevice(prev);

@@ -9,8 +9,9 @@ Mirrors `EmbeddingLayer`, `UserTower`, `AdTower`, `TwoTowerModel` of the referen
 The parameters are ordinary torch modules (containers only).  The arithmetic of `forward`
 is NOT torch: in eval mode on a CUDA device it runs libb2retr.so -
   EmbeddingLayer.forward -> b2r_gather_concat           (bit-exact fp32 row gather + concat)
-  UserTower/AdTower.forward -> b2r_tower_forward         (gather -> 3 tcgen05 GEMMs with
-       BatchNorm folded into W/b, bias+ReLU from TMEM, fp32 L2-normalise epilogue)
+  UserTower/AdTower.forward -> b2r_tower_forward         (ONE fused kernel: gather -> 3 chained
+       tcgen05 GEMMs with BatchNorm folded into W/b, hidden activations kept in shared memory,
+       bias+ReLU from TMEM, fp32 L2-normalise epilogue; no host sync per call - see _DeviceFlags)
 Training (`.train()` mode, autograd, TwoTowerLoss) is outside the hot-path scope and raises;
 so does a CPU tensor: there is no CPU fallback.
 """
@@ -41,11 +42,50 @@ def _need_cuda_eval(module: nn.Module, t: torch.Tensor, what: str) -> None:
                            "(there is no CPU fallback)")
 
 
+class _DeviceFlags:
+    """Status word a tower / gather kernel ORs bits into, read WITHOUT a host sync on the hot path.
+
+    The kernels report a bad categorical id (torch: IndexError) and fp16 saturation through one int32 on
+    the device.  Reading it with `.item()` would cost a device->host synchronisation per forward - at B = 1
+    (`recommend_ads`, inference.py:223-227) that IS the latency.  So every forward enqueues an async copy of
+    the word into pinned host memory plus an event; the word is inspected
+      * synchronously on the FIRST forward after the weights (re)loaded - a checkpoint whose activations
+        leave the fp16 range does so on its first batch, and so does a mis-built id vocabulary;
+      * otherwise at the start of the next forward (event already complete: no wait) or in `check()`.
+    `sync_checks = True` on the owning module restores a check (and a sync) on every call."""
+
+    def __init__(self, device):
+        self.dev = torch.zeros(1, dtype=torch.int32, device=device)
+        self.host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.event = None
+
+    def publish(self):
+        """enqueue device -> pinned copy on the current stream"""
+        self.host.copy_(self.dev, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record(torch.cuda.current_stream(self.dev.device))
+
+    def poll(self, wait: bool) -> int:
+        """bits seen so far (0 when nothing is pending or, without `wait`, not yet known); clears them"""
+        if self.event is None:
+            return 0
+        if wait:
+            self.event.synchronize()
+        elif not self.event.query():
+            return 0
+        self.event = None
+        bits = int(self.host[0])
+        if bits:
+            self.dev.zero_()
+        return bits
+
+
 class EmbeddingLayer(nn.Module):
     """One `nn.Embedding(card, embedding_dim)` per categorical field, looked up and
     concatenated in dict order (reference two_tower_model.py:12-49)."""
 
-    check_indices = True  # torch raises IndexError on an out-of-range id; we do the same
+    check_indices = True  # torch raises IndexError on an out-of-range id; so do we (see _DeviceFlags for when)
+    sync_checks = None    # None: first forward after a table change is checked synchronously, later ones deferred
 
     def __init__(self, feature_dims: Dict[str, int], embedding_dim: int = 16):
         super().__init__()
@@ -54,6 +94,13 @@ class EmbeddingLayer(nn.Module):
         self.embedding_dim = embedding_dim
         self.num_features = len(feature_dims)
         self._ptr_cache = None
+        self._flags = None
+        self._fresh = True
+
+    def check(self) -> None:
+        """Wait for the pending gathers and raise what they reported."""
+        if self._flags is not None and self._flags.poll(wait=True) & _lib.TOWER_BAD_INDEX:
+            raise IndexError("index out of range in self")
 
     def _tables(self, device):
         """(device ptr array, device cards array, keep-alive) for the current weights."""
@@ -66,6 +113,8 @@ class EmbeddingLayer(nn.Module):
             ptrs = torch.tensor([w.data_ptr() for w in ws], dtype=torch.int64, device=device)
             cards = torch.tensor([w.shape[0] for w in ws], dtype=torch.int64, device=device)
             self._ptr_cache = (sig, ptrs, cards)
+            self._flags = _DeviceFlags(device)
+            self._fresh = True
         return self._ptr_cache[1], self._ptr_cache[2]
 
     def forward(self, categorical_features: torch.Tensor) -> torch.Tensor:
@@ -79,14 +128,19 @@ class EmbeddingLayer(nn.Module):
         if F != self.num_features:
             cat = cat[:, :self.num_features].contiguous()
         ptrs, cards = self._tables(dev)
+        flags = self._flags
+        if self.check_indices and flags.poll(wait=False) & _lib.TOWER_BAD_INDEX:
+            raise IndexError("index out of range in self (reported by an earlier forward)")
         out = torch.empty((B, self.num_features * self.embedding_dim), dtype=torch.float32, device=dev)
-        err = torch.zeros(1, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(lib.b2r_gather_concat(ptrs.data_ptr(), cards.data_ptr(), self.num_features,
                                              self.embedding_dim, cat.data_ptr(), B, out.data_ptr(),
-                                             out.shape[1], err.data_ptr(), _stream(dev)))
-        if self.check_indices and int(err.item()) != 0:
-            raise IndexError("index out of range in self")
+                                             out.shape[1], flags.dev.data_ptr(), _stream(dev)))
+            if self.check_indices:
+                flags.publish()
+                if self.sync_checks or (self.sync_checks is None and self._fresh):
+                    self._fresh = False
+                    self.check()
         return out
 
 
@@ -119,6 +173,9 @@ class _Tower(nn.Module):
     """Shared body of UserTower / AdTower (reference two_tower_model.py:52-184)."""
 
     check_indices = True
+    sync_checks = None    # see _DeviceFlags: None = synchronous check on the first forward after (re)loading weights
+    operand_dtype = None  # None: fp16 operands, bf16 once a saturation is seen; "fp16" / "bf16" pin the format
+    force_path = 0        # tests: 1 = layer-by-layer kernels, 2 = fused kernel
 
     def _build(self, feature_dims: Dict[str, int], numerical_dim: int, embedding_dim: int,
                hidden_dims: List[int], output_dim: int, dropout: float) -> None:
@@ -135,13 +192,19 @@ class _Tower(nn.Module):
         self._handle = None
         self._handle_sig = None
         self._keep = None
+        self._flags = None
+        self._fresh = True
+        self._ws = None
+        self._tensors = None
 
     # -- native handle, rebuilt whenever a parameter/buffer changes ---------------------
     def _signature(self, device):
-        items = []
-        for t in list(self.parameters()) + list(self.buffers()):
-            items.append((t.data_ptr(), t._version))
-        return (str(device), tuple(items))
+        """Cheap change detector (runs on every forward): the in-place version counters of every parameter
+        and buffer.  Storage moves (.to / .cuda / load_state_dict(assign=True)) go through `_apply` /
+        `_load_from_state_dict`, which drop the handle explicitly."""
+        if self._tensors is None:
+            self._tensors = list(self.parameters()) + list(self.buffers())
+        return (device, tuple(t._version for t in self._tensors))
 
     def _native(self, device):
         sig = self._signature(device)
@@ -170,10 +233,47 @@ class _Tower(nn.Module):
         h = C.c_void_p()
         with torch.cuda.device(device):
             _lib.check(lib.b2r_tower_create(C.byref(h), C.byref(tw), device.index or 0))
+            if self.operand_dtype is not None:
+                _lib.check(lib.b2r_tower_set_param(h, b"operand_dtype", {"fp16": 0.0, "bf16": 1.0}[self.operand_dtype]))
+            if self.force_path:
+                _lib.check(lib.b2r_tower_set_param(h, b"force_path", float(self.force_path)))
         self._handle, self._handle_sig = h, sig
+        self._flags = _DeviceFlags(device)
+        self._fresh = True
         return h
 
+    @property
+    def native_operand_dtype(self) -> str:
+        """'fp16' or 'bf16': what the tensor cores are fed right now (None before the first forward)."""
+        if self._handle is None:
+            return None
+        return "bf16" if _lib.load().b2r_tower_get_param(self._handle, b"operand_dtype") == 1.0 else "fp16"
+
+    def _handle_bits(self, bits: int, deferred: bool) -> bool:
+        """React to the status bits of an earlier (deferred) or the current forward.  Returns True when the
+        caller should rerun the current batch (operands switched to bf16)."""
+        if bits & _lib.TOWER_BAD_INDEX and self.check_indices:
+            raise IndexError("index out of range in self" + (" (reported by an earlier forward)" if deferred else ""))
+        if bits & _lib.TOWER_SATURATED and self.operand_dtype != "fp16":
+            import warnings
+            _lib.check(_lib.load().b2r_tower_set_param(self._handle, b"operand_dtype", 1.0))
+            warnings.warn(f"{type(self).__name__}: an fp16 tensor-core operand exceeded +-65504 "
+                          + ("in an earlier forward (its output was clipped); " if deferred else "; ")
+                          + "switching this tower to bf16 operands")
+            return True
+        return False
+
+    def check(self) -> None:
+        """Wait for the pending forwards and raise / react to what they reported."""
+        if self._flags is not None and self._handle is not None:
+            self._handle_bits(self._flags.poll(wait=True), deferred=True)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._free()
+        return super()._load_from_state_dict(*a, **k)
+
     def _free(self):
+        self._tensors = None
         if getattr(self, "_handle", None) is not None:
             try:
                 _lib.load().b2r_tower_destroy(self._handle)
@@ -207,15 +307,23 @@ class _Tower(nn.Module):
         out = torch.empty((B, self.output_dim), dtype=torch.float32, device=dev)
         if B == 0:
             return out
-        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        flags = self._flags
         with torch.cuda.device(dev):
-            need = int(lib.b2r_tower_workspace(h, B))
-            ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
-            _lib.check(lib.b2r_tower_forward(h, cat.data_ptr(), num.data_ptr() if self._numerical_dim else None,
-                                             B, out.data_ptr(), err.data_ptr(), ws.data_ptr(), ws.numel(),
-                                             _stream(dev)))
-        if self.check_indices and int(err.item()) != 0:
-            raise IndexError("index out of range in self")
+            self._handle_bits(flags.poll(wait=False), deferred=True)     # what earlier forwards reported (no wait)
+            for attempt in range(2):
+                need = int(lib.b2r_tower_workspace(h, B))     # 0 on the fused path
+                if need and (self._ws is None or self._ws.numel() < need or self._ws.device != dev):
+                    self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+                _lib.check(lib.b2r_tower_forward(h, cat.data_ptr(), num.data_ptr() if self._numerical_dim else None,
+                                                 B, out.data_ptr(), flags.dev.data_ptr(),
+                                                 self._ws.data_ptr() if need else None, need, _stream(dev)))
+                flags.publish()
+                if not (self.sync_checks or (self.sync_checks is None and self._fresh)):
+                    break
+                # first forward on these weights: look at the status now; a saturated batch is rerun in bf16
+                if not self._handle_bits(flags.poll(wait=True), deferred=False):
+                    break
+            self._fresh = False
         return out
 
 

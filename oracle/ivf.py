@@ -46,9 +46,29 @@ def kmeans(x: np.ndarray, k: int, niter: int = 10, seed: int = 1234, spherical: 
     return cent.astype(np.float32)
 
 
+def assign_max_ip(x: np.ndarray, centroids: np.ndarray, chunk: int = 1 << 16) -> np.ndarray:
+    """argmax_c <x, centroid_c> per row (the IndexFlatIP quantiser), computed chunk by chunk so that a
+    10M-row corpus never materialises its [n, nlist] score matrix; ties -> lowest list id (np.argmax)."""
+    out = np.empty(len(x), dtype=np.int64)
+    ct = np.ascontiguousarray(centroids.T)
+    for lo in range(0, len(x), chunk):
+        out[lo:lo + chunk] = np.argmax(x[lo:lo + chunk] @ ct, axis=1)
+    return out
+
+
+def rows_by_list(assign: np.ndarray, nlist: int):
+    """(order, offsets): rows of list l, ascending, are order[offsets[l]:offsets[l+1]] — the same row sets
+    as `np.nonzero(assign == l)`, found once instead of once per (query, list)."""
+    order = np.argsort(assign, kind="stable")
+    offsets = np.zeros(nlist + 1, dtype=np.int64)
+    np.cumsum(np.bincount(assign, minlength=nlist), out=offsets[1:])
+    return order, offsets
+
+
 class OracleIndexIVFFlat:
     def __init__(self, d: int, nlist: int, **_):
         self.d, self.nlist = d, nlist
+        self._by_list = None
         self.nprobe = 1
         self.centroids = None
         self.xb = np.zeros((0, d), dtype=np.float32)
@@ -74,7 +94,8 @@ class OracleIndexIVFFlat:
     def add(self, x) -> None:
         x = np.ascontiguousarray(x, dtype=np.float32)
         self.xb = np.concatenate([self.xb, x])
-        self.assign = np.concatenate([self.assign, np.argmax(x @ self.centroids.T, axis=1)])
+        self.assign = np.concatenate([self.assign, assign_max_ip(x, self.centroids)])
+        self._by_list = None
 
     def list_sizes(self) -> np.ndarray:
         return np.bincount(self.assign, minlength=self.nlist).astype(np.int64)
@@ -91,8 +112,11 @@ class OracleIndexIVFFlat:
         D = np.full((len(q), kk), NEG_FLT_MAX, dtype=np.float32)
         I = np.full((len(q), kk), -1, dtype=np.int64)
         lists = self.probe(q)
+        if self._by_list is None or self._by_list[2] != len(self.assign):
+            self._by_list = rows_by_list(self.assign, self.nlist) + (len(self.assign),)
+        order_l, off = self._by_list[:2]
         for qi in range(len(q)):
-            rows = np.nonzero(np.isin(self.assign, lists[qi]))[0]
+            rows = np.sort(np.concatenate([order_l[off[l]:off[l + 1]] for l in lists[qi]]))
             if rows.size == 0:
                 continue
             s = self.xb[rows] @ q[qi]

@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .ivf import kmeans
+from .ivf import assign_max_ip, kmeans, rows_by_list
 
 FLT_MAX = np.float32(3.4028234663852886e38)
 
@@ -83,7 +83,7 @@ class OracleIndexIVFPQ:
 
     def add(self, x, codes=None):
         x = np.ascontiguousarray(x, dtype=np.float32)
-        a = np.argmax(x @ self.centroids.T, axis=1)
+        a = assign_max_ip(x, self.centroids)
         c = self.encode(x, a) if codes is None else np.ascontiguousarray(codes, dtype=np.uint8)
         self.assign = np.concatenate([self.assign, a])
         self.codes = np.concatenate([self.codes, c])
@@ -98,11 +98,12 @@ class OracleIndexIVFPQ:
         I = np.full((len(q), kk), -1, dtype=np.int64)
         S = q @ self.centroids.T
         npb = min(self.nprobe, self.nlist)
+        order_l, off = rows_by_list(self.assign, self.nlist)
         for qi in range(len(q)):
             lists = np.lexsort((np.arange(self.nlist), -S[qi]))[:npb]
             rows_all, dist_all = [], []
             for l in lists:
-                rows = np.nonzero(self.assign == l)[0]
+                rows = order_l[off[l]:off[l + 1]]
                 if rows.size == 0:
                     continue
                 res = (q[qi] - self.centroids[l]).reshape(self.m, self.dsub)

@@ -109,3 +109,102 @@ def test_config4_shape_gather_26_fields_large_tables(built_lib):
     sel = slice(0, 64)
     ref_out = otowers.tower_forward(state, "user_tower", cat[sel].cpu().numpy(), num[sel].cpu().numpy())
     assert np.abs(out[sel].cpu().numpy() - ref_out).max() < TOWER_ATOL
+
+
+@pytest.mark.parametrize("cfg_name", ["cfg1", "small"])
+@pytest.mark.parametrize("B", [1, 129, 1000, 20000])
+def test_fused_kernel_and_layerwise_kernels_agree(built_lib, cfg_name, B):
+    """The one-kernel tower (gather -> 3 chained tcgen05 GEMMs, activations in shared memory) and the
+    layer-by-layer kernels compute the same 16-bit-operand / fp32-accumulate arithmetic: both within the
+    tolerance of the fp32 oracle and within fp32 summation-order noise of each other."""
+    import torch
+    from oracle import towers as otowers
+    from weights import make_inputs
+    m, fx, cfg, state = _model(cfg_name)
+    ucat, unum, acat = make_inputs(cfg, 99 + B, B)
+    outs = {}
+    for path in (1, 2):
+        for tower in (m.user_tower, m.ad_tower):
+            tower.force_path = path
+            tower._free()
+        with torch.no_grad():
+            u = m.get_user_embeddings(torch.from_numpy(ucat).cuda(), torch.from_numpy(unum).cuda()).cpu().numpy()
+            a = m.get_ad_embeddings(torch.from_numpy(acat).cuda()).cpu().numpy()
+        lib = built_lib
+        assert lib.b2r_tower_get_param(m.user_tower._handle, b"fused") == (1.0 if path == 2 else 0.0)
+        outs[path] = (u, a)
+    n_ref = min(B, 2000)
+    ref_u = otowers.tower_forward(state, "user_tower", ucat[:n_ref], unum[:n_ref])
+    ref_a = otowers.tower_forward(state, "ad_tower", acat[:n_ref])
+    for path in (1, 2):
+        assert np.abs(outs[path][0][:n_ref] - ref_u).max() < TOWER_ATOL
+        assert np.abs(outs[path][1][:n_ref] - ref_a).max() < TOWER_ATOL
+        np.testing.assert_allclose(np.linalg.norm(outs[path][0], axis=1), 1.0, atol=1e-5)
+    assert np.abs(outs[1][0] - outs[2][0]).max() < 2e-6
+    assert np.abs(outs[1][1] - outs[2][1]).max() < 2e-6
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_fp16_saturation_is_detected_and_rerun_in_bf16(built_lib, path):
+    """A checkpoint whose hidden activations leave the fp16 range (first Linear scaled x 2e5) must not be
+    silently clipped: the first forward reports the saturation, the tower switches to bf16 operands
+    (north_star's format) and reruns the batch; the result tracks the fp32 oracle."""
+    import torch
+    from movie_recommender_demo_b200.two_tower_model import TwoTowerModel
+    from oracle import towers as otowers
+    from weights import CONFIGS, feature_dims, make_inputs, make_state
+    cfg = CONFIGS["small"]
+    user, ad = feature_dims(cfg)
+    state = {k: np.asarray(v).copy() for k, v in make_state(cfg, 5).items()}
+    for k in ("user_tower.mlp.0.weight", "user_tower.mlp.0.bias"):
+        state[k] = state[k] * np.float32(2e5)
+    m = TwoTowerModel(user, ad, cfg["numerical_dim"], cfg["embedding_dim"], cfg["hidden_dims"], cfg["output_dim"])
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()})
+    m = m.to("cuda").eval()
+    m.user_tower.force_path = path
+    ucat, unum, _ = make_inputs(cfg, 3, 300)
+    ref = otowers.tower_forward(state, "user_tower", ucat, unum)
+    with pytest.warns(UserWarning, match="bf16"):
+        u = m.get_user_embeddings(torch.from_numpy(ucat).cuda(), torch.from_numpy(unum).cuda()).cpu().numpy()
+    assert m.user_tower.native_operand_dtype == "bf16"
+    assert np.abs(u - ref).max() < 2e-2          # bf16 operands: 8x the fp16 rounding error per layer
+    cos = (u * ref).sum(1)
+    assert cos.min() > 0.999
+    # pinned to fp16 the same checkpoint clips: the flag is still raised, the answer is visibly off
+    m2 = TwoTowerModel(user, ad, cfg["numerical_dim"], cfg["embedding_dim"], cfg["hidden_dims"], cfg["output_dim"])
+    m2.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()})
+    m2 = m2.to("cuda").eval()
+    m2.user_tower.force_path = path
+    m2.user_tower.operand_dtype = "fp16"
+    u16 = m2.get_user_embeddings(torch.from_numpy(ucat).cuda(), torch.from_numpy(unum).cuda()).cpu().numpy()
+    assert m2.user_tower.native_operand_dtype == "fp16"
+    assert np.abs(u16 - ref).max() > np.abs(u - ref).max()
+
+
+def test_index_check_is_deferred_after_the_first_forward(built_lib):
+    """No host sync per forward: the first forward on fresh weights is checked synchronously, later ones report
+    a bad id at the next forward or in check() (torch on CUDA reports it asynchronously too)."""
+    import torch
+    m, fx, cfg, _ = _model("small")
+    good = torch.from_numpy(fx["ucat"]).cuda()
+    num = torch.from_numpy(fx["unum"]).cuda()
+    ref = m.get_user_embeddings(good, num)
+    bad = fx["ucat"].copy()
+    bad[1, 0] = -1
+    out = m.get_user_embeddings(torch.from_numpy(bad).cuda(), num)      # returns: the check is deferred
+    assert out.shape == ref.shape
+    with pytest.raises(IndexError):
+        m.user_tower.check()
+    assert torch.equal(m.get_user_embeddings(good, num), ref)            # flag was cleared
+    m.get_user_embeddings(torch.from_numpy(bad).cuda(), num)
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError, match="earlier forward"):
+        m.get_user_embeddings(good, num)
+    m.user_tower.sync_checks = True
+    with pytest.raises(IndexError):
+        m.get_user_embeddings(torch.from_numpy(bad).cuda(), num)
+    emb = m.user_tower.embedding_layer
+    emb(good)
+    emb(torch.from_numpy(bad).cuda())
+    with pytest.raises(IndexError):
+        emb.check()
