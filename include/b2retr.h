@@ -175,6 +175,18 @@ int b2r_index_get_vectors(const b2r_index* h, int64_t row0, int64_t n, float* ou
 int b2r_topk_merge(int P, int q, int k, const float* D_all, const int64_t* I_all, float* D_out,
                    int64_t* I_out, int largest, void* stream);
 
+/* The same exchange with ONE buffer per rank and 8 instead of 12 bytes per result: b2r_topk_pack writes, per
+ * query row, [k scores (fp32 bits)] [k LOCAL labels int32 = I - label_base, -1 for empty slots] [status]
+ * (2k+1 int32).  Rows q..q_rows-1 are filled as empty lists (padding so that q_rows splits evenly into per-rank
+ * query slices for an all-to-all).  After the collective, b2r_topk_merge_packed merges rows [0,q) of P such
+ * blocks (block s starts at packed + s*q_stride*(2k+1), its labels get bases[s] added back; bases is a DEVICE
+ * array of P int64) into best-first D_out/I_out and ORs the P status words into status_out (may be NULL).
+ * Same result, tie order included, as b2r_topk_merge on the unpacked lists. */
+int b2r_topk_pack(int q, int q_rows, int k, const float* D, const int64_t* I, const int32_t* status,
+                  int64_t label_base, int32_t* out, int largest, void* stream);
+int b2r_topk_merge_packed(int P, int q, int q_stride, int k, const int32_t* packed, const int64_t* bases,
+                          float* D_out, int64_t* I_out, int32_t* status_out, int largest, void* stream);
+
 /* ---------------------------------------------------------------- tower -- */
 
 /* Replaces EmbeddingLayer.forward (two_tower_model.py:42-47): F per-field row

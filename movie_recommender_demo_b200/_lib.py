@@ -87,6 +87,8 @@ def load():
         "b2r_index_get_codes": (i32, [vp, i64, i64, vp, vp]),
         "b2r_index_add_codes": (i32, [vp, i64, vp, vp, vp]),
         "b2r_topk_merge": (i32, [i32, i32, i32, vp, vp, vp, vp, i32, vp]),
+        "b2r_topk_pack": (i32, [i32, i32, i32, vp, vp, vp, i64, vp, i32, vp]),
+        "b2r_topk_merge_packed": (i32, [i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]),
         "b2r_gather_concat": (i32, [vp, vp, i32, i32, vp, i64, vp, i64, vp, vp]),
         "b2r_tower_create": (i32, [C.POINTER(vp), C.POINTER(TowerWeights), i32]),
         "b2r_tower_destroy": (i32, [vp]),

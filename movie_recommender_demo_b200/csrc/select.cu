@@ -554,6 +554,84 @@ topk_merge_kernel(int P, int k, const float* __restrict__ D_all, const int64_t* 
   }
 }
 
+
+// ------------------------------------------------- packed shard exchange (multi-GPU) ---
+// One row per query: [k scores (fp32 bits)] [k LOCAL labels (int32, -1 = empty slot)] [status], i.e. 8 bytes per
+// result instead of the 12 of (fp32 score, int64 global label): the shard's label base is added back after
+// the exchange.  One buffer = ONE collective.
+__global__ void __launch_bounds__(256)
+topk_pack_kernel(int q, int q_rows, int k, const float* __restrict__ D, const int64_t* __restrict__ I,
+                 const int32_t* __restrict__ status, int64_t base, int32_t* __restrict__ out, int largest) {
+  const int W = 2 * k + 1;
+  for (int row = blockIdx.x; row < q_rows; row += gridDim.x) {
+    int32_t* o = out + (size_t)row * W;
+    if (row < q) {
+      for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        const int64_t lab = I[(size_t)row * k + j];
+        o[j] = __float_as_int(D[(size_t)row * k + j]);
+        o[k + j] = lab < 0 ? -1 : (int32_t)(lab - base);
+      }
+      if (threadIdx.x == 0) o[2 * k] = status ? status[row] : 0;
+    } else {   // padding rows of the last query slice: empty lists
+      for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        o[j] = __float_as_int(largest ? -FLT_MAX : FLT_MAX);
+        o[k + j] = -1;
+      }
+      if (threadIdx.x == 0) o[2 * k] = 0;
+    }
+  }
+}
+
+// Merge P best-first lists of k per query by RANKING instead of sorting: entry (shard s, position j) precedes
+// entry (t, i) iff its score is better, or equal with (s, j) < (t, i) - the same total order as the bitonic
+// merge above (and as an unsharded search: lower shard = lower labels).  Its output slot is
+//   j + sum over t != s of #{entries of list t that precede it},
+// each count a binary search in a sorted list: no barriers, every thread independent.
+// packed: [P, q_stride rows, 2k+1]; this launch merges rows [0, q) of every shard's block.
+__global__ void __launch_bounds__(kSelThreads)
+topk_merge_packed_kernel(int P, int k, const int32_t* __restrict__ packed, size_t shard_stride,
+                         const int64_t* __restrict__ bases, float* __restrict__ D_out,
+                         int64_t* __restrict__ I_out, int32_t* __restrict__ status_out, int largest) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  float* sc = reinterpret_cast<float*>(sm);   // [P][k] scores, sign-normalised so that larger is better
+  const int q = blockIdx.x;
+  const int W = 2 * k + 1;
+  const int n = P * k;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int s = i / k, j = i - s * k;
+    const float v = __int_as_float(packed[(size_t)s * shard_stride + (size_t)q * W + j]);
+    sc[i] = largest ? v : -v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int s = i / k, j = i - s * k;
+    const float v = sc[i];
+    int rank = j;
+    for (int t = 0; t < P && rank < k; ++t) {
+      if (t == s) continue;
+      const float* lt = sc + t * k;
+      // lists are descending: count entries > v (t > s) or >= v (t < s)
+      int lo = 0, hi = k;
+      if (t < s) {
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (lt[mid] >= v) lo = mid + 1; else hi = mid; }
+      } else {
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (lt[mid] > v) lo = mid + 1; else hi = mid; }
+      }
+      rank += lo;
+    }
+    if (rank < k) {
+      const int32_t lab = packed[(size_t)s * shard_stride + (size_t)q * W + k + j];
+      D_out[(size_t)q * k + rank] = largest ? v : -v;
+      I_out[(size_t)q * k + rank] = lab < 0 ? -1 : bases[s] + (int64_t)lab;
+    }
+  }
+  if (status_out && threadIdx.x == 0) {
+    int st = 0;
+    for (int s = 0; s < P; ++s) st |= packed[(size_t)s * shard_stride + (size_t)q * W + 2 * k];
+    status_out[q] = st;
+  }
+}
+
 }  // namespace
 
 int launch_kth_value(const float* vals, int rows, int64_t T, int64_t ld, int m, float* tau,
@@ -625,5 +703,37 @@ extern "C" int b2r_topk_merge(int P, int q, int k, const float* D_all, const int
   topk_merge_kernel<<<q, kSelThreads, smem, (cudaStream_t)stream>>>(
       P, k, D_all, I_all, (size_t)q * k, D_out, I_out, largest);
   B2R_CHECK_LAUNCH("topk_merge_kernel");
+  return B2R_OK;
+}
+
+extern "C" int b2r_topk_pack(int q, int q_rows, int k, const float* D, const int64_t* I, const int32_t* status,
+                             int64_t label_base, int32_t* out, int largest, void* stream) {
+  using namespace b2r;
+  if (q < 0 || q_rows < q || k < 1 || (q > 0 && (!D || !I)) || (q_rows > 0 && !out))
+    return fail(B2R_EINVAL, "topk_pack: bad arguments");
+  if (q_rows == 0) return B2R_OK;
+  const int grid = q_rows < 148 * 8 ? q_rows : 148 * 8;
+  topk_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q, q_rows, k, D, I, status, label_base, out, largest);
+  B2R_CHECK_LAUNCH("topk_pack_kernel");
+  return B2R_OK;
+}
+
+extern "C" int b2r_topk_merge_packed(int P, int q, int q_stride, int k, const int32_t* packed, const int64_t* bases,
+                                     float* D_out, int64_t* I_out, int32_t* status_out, int largest, void* stream) {
+  using namespace b2r;
+  if (P < 1 || q < 0 || q_stride < q || k < 1 || !bases) return fail(B2R_EINVAL, "topk_merge_packed: bad arguments");
+  if ((int64_t)P * k > 16384) return fail(B2R_EUNSUPPORTED, "topk_merge_packed: P*k must be <= 16384");
+  if (q == 0) return B2R_OK;
+  const size_t smem = (size_t)P * k * 4;
+  static bool configured[64] = {};
+  int dev = 0;
+  B2R_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    B2R_CUDA(cudaFuncSetAttribute(topk_merge_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4));
+    configured[dev & 63] = true;
+  }
+  topk_merge_packed_kernel<<<q, kSelThreads, smem, (cudaStream_t)stream>>>(
+      P, k, packed, (size_t)q_stride * (2 * k + 1), bases, D_out, I_out, status_out, largest);
+  B2R_CHECK_LAUNCH("topk_merge_packed_kernel");
   return B2R_OK;
 }

@@ -493,3 +493,55 @@ def test_hnsw_rejects_rows_it_cannot_rank_and_reads_faiss_files(fr, tmp_path):
     assert ids[:, 0].tolist() == [11, 4321] and np.allclose(dist[:, 0], 0.0, atol=2e-6)
     want = np.sort(((x[11][None] - x) ** 2).sum(1))[:5]
     assert np.allclose(dist[0], want, atol=4e-6)
+
+
+@pytest.mark.parametrize("P,Q,k,q_rows", [(4, 9, 100, 9), (8, 37, 500, 40), (2, 300, 64, 300), (3, 5, 1000, 6)])
+def test_packed_exchange_kernels_match_unsharded(fr, built_lib, P, Q, k, q_rows):
+    """b2r_topk_pack + b2r_topk_merge_packed (the one-buffer, 8-bytes-per-result shard exchange, ranking merge)
+    on P logical shards of one device == the unsharded search == b2r_topk_merge on the unpacked lists;
+    status words are OR-ed; padding rows (q..q_rows) are empty lists."""
+    import torch
+    from movie_recommender_demo_b200 import _lib
+    rng = np.random.default_rng(P * 1000 + Q)
+    N, d = 50000, 64
+    x = rng.standard_normal((N, d)).astype(np.float32)
+    x[20000:20020] = x[3]                                   # exact ties, some across shard boundaries
+    x[N // P - 3: N // P + 3] = x[5]
+    q = rng.standard_normal((Q, d)).astype(np.float32)
+    q[0] = x[3]
+    q[1] = x[5]
+    full = fr.IndexFlatIP(d)
+    full.add(x, normalize=True)
+    Dref, Iref = full.search(q, k, normalize=True)
+    W = 2 * k + 1
+    sp = int(torch.cuda.current_stream().cuda_stream)
+    packed = torch.empty((P, q_rows, W), dtype=torch.int32, device="cuda")
+    bases, Ds, Is, want_st = [], [], [], np.zeros(Q, dtype=np.int32)
+    for s in range(P):
+        lo, hi = s * N // P, (s + 1) * N // P
+        sh = fr.IndexFlatIP(d)
+        sh.add(x[lo:hi], normalize=True)
+        sh.set_label_base(lo)
+        D, I = sh.search(q, k, normalize=True, return_device=True)
+        st = torch.zeros(Q, dtype=torch.int32, device="cuda")
+        st[s::3] = 1 << (s % 4)
+        want_st[s::3] |= 1 << (s % 4)
+        _lib.check(built_lib.b2r_topk_pack(Q, q_rows, k, D.data_ptr(), I.data_ptr(), st.data_ptr(), lo,
+                                           packed[s].data_ptr(), 1, sp))
+        bases.append(lo), Ds.append(D), Is.append(I)
+    bases_t = torch.tensor(bases, dtype=torch.int64, device="cuda")
+    D_out = torch.empty((q_rows, k), dtype=torch.float32, device="cuda")
+    I_out = torch.empty((q_rows, k), dtype=torch.int64, device="cuda")
+    st_out = torch.empty(q_rows, dtype=torch.int32, device="cuda")
+    _lib.check(built_lib.b2r_topk_merge_packed(P, q_rows, q_rows, k, packed.data_ptr(), bases_t.data_ptr(),
+                                               D_out.data_ptr(), I_out.data_ptr(), st_out.data_ptr(), 1, sp))
+    assert np.array_equal(I_out[:Q].cpu().numpy(), Iref)
+    assert np.array_equal(D_out[:Q].cpu().numpy(), Dref)
+    assert np.array_equal(st_out[:Q].cpu().numpy(), want_st)
+    assert (I_out[Q:] == -1).all() and (st_out[Q:] == 0).all()
+    if P * k <= 8192:
+        D2 = torch.empty((Q, k), dtype=torch.float32, device="cuda")
+        I2 = torch.empty((Q, k), dtype=torch.int64, device="cuda")
+        _lib.check(built_lib.b2r_topk_merge(P, Q, k, torch.stack(Ds).contiguous().data_ptr(),
+                                            torch.stack(Is).contiguous().data_ptr(), D2.data_ptr(), I2.data_ptr(), 1, sp))
+        assert torch.equal(I2, I_out[:Q]) and torch.equal(D2, D_out[:Q])
