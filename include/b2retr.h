@@ -167,6 +167,15 @@ int b2r_index_get_labels(const b2r_index* h, int64_t row0, int64_t n, int64_t* o
  * replaces what faiss.write_index serialises, faiss_retrieval.py:203-206). */
 int b2r_index_get_vectors(const b2r_index* h, int64_t row0, int64_t n, float* out, void* stream);
 
+/* Replaces `faiss.write_index(index, path)` / `faiss.read_index(path)` (faiss_retrieval.py:203-206, :226) for
+ * hosts that do not speak faiss's own file layout (the Python shim reads/writes that one, faiss_io.py): a
+ * self-contained native container - header, coarse centroids, PQ codebooks, rows (or codes + list ids) in
+ * insertion order, id map.  `path` is a host string.  save synchronises `stream`; load creates a NEW handle
+ * on `device` that searches exactly like the saved one (same rows, same 16-bit scan format, same lists,
+ * same id map).  The reference's pickled `.metadata` side-car stays the Python wrapper's business. */
+int b2r_index_save(const b2r_index* h, const char* path, void* stream);
+int b2r_index_load(b2r_index** out, const char* path, int device, void* stream);
+
 /* ------------------------------------------------------------ multi-GPU -- */
 
 /* Merge P per-shard results (after the NCCL all-gather).

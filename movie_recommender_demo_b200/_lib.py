@@ -86,6 +86,8 @@ def load():
         "b2r_index_get_labels": (i32, [vp, i64, i64, vp, vp]),
         "b2r_index_get_codes": (i32, [vp, i64, i64, vp, vp]),
         "b2r_index_add_codes": (i32, [vp, i64, vp, vp, vp]),
+        "b2r_index_save": (i32, [vp, C.c_char_p, vp]),
+        "b2r_index_load": (i32, [C.POINTER(vp), C.c_char_p, i32, vp]),
         "b2r_topk_merge": (i32, [i32, i32, i32, vp, vp, vp, vp, i32, vp]),
         "b2r_topk_pack": (i32, [i32, i32, i32, vp, vp, vp, i64, vp, i32, vp]),
         "b2r_topk_merge_packed": (i32, [i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]),

@@ -641,6 +641,19 @@ struct DevBuf {  // RAII cudaMalloc scratch (build-time paths only; search never
   template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
+// scoped override of a flat index's path choice (0 auto, 1 dense, 2 filter)
+struct ForcePath {
+  b2r_index* h;
+  int keep;
+  ForcePath(b2r_index* h_, int v) : h(h_), keep(h_->force_path) { h->force_path = v; }
+  ~ForcePath() { h->force_path = keep; }
+};
+
+__global__ void or_status_kernel(int32_t* __restrict__ dst, const int32_t* __restrict__ src, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] |= src[i];
+}
+
 // exact top-1 (or top-k) centroid of every row of x through the nested flat quantiser
 int quantizer_assign(b2r_index* h, int64_t n, const float* x, int normalize, int k, int64_t* labels,
                      cudaStream_t stream) {
@@ -930,6 +943,7 @@ namespace {
 struct IvfPlan {
   int nprobe = 1, chunk = 0, qpad = 0, max_units = 0, cap = 4096, c_target = 0, sample_stride = 1;
   int64_t smax = 0, pairs_pad = 0;
+  size_t off_cstatus = 0;
   size_t off_q16, off_q32, off_qnorm, off_coarse, off_cdist, off_pair_out, off_row_len, off_listcnt, off_pairoff,
       off_cursor, off_pair_sorted, off_gq16, off_units, off_nunits, off_tau, off_count, off_cand, off_score,
       off_qws, off_qtab, qws_bytes, total;
@@ -983,6 +997,7 @@ IvfPlan make_ivf_plan(const b2r_index* h, int q, int k, int nprobe) {
   pl.off_qnorm = take((size_t)pl.qpad * 4);
   pl.off_coarse = take((size_t)pairs * 8);
   pl.off_cdist = take((size_t)pairs * 4);
+  pl.off_cstatus = take((size_t)pl.chunk * 4);
   pl.off_pair_out = take((size_t)pairs * 8);
   pl.off_row_len = take((size_t)pl.chunk * 4);
   pl.off_listcnt = take((size_t)h->nlist * 4);
@@ -996,7 +1011,12 @@ IvfPlan make_ivf_plan(const b2r_index* h, int q, int k, int nprobe) {
   pl.off_count = take((size_t)pl.chunk * 4);
   pl.off_cand = take((size_t)pl.chunk * pl.cap * 8);
   pl.off_score = take((size_t)pl.chunk * pl.smax * 4);
-  pl.qws_bytes = flat_search_workspace(h->quantizer, pl.chunk, nprobe);
+  {
+    // the search-time coarse quantiser always takes the flat index's DENSE path (dump + exact k-th): nlist <= 65536
+    // always fits, and the probed list set must never depend on a sampled threshold (see ivf_search)
+    ForcePath dense(h->quantizer, 1);
+    pl.qws_bytes = flat_search_workspace(h->quantizer, pl.chunk, nprobe);
+  }
   pl.off_qws = take(pl.qws_bytes);
   pl.off_qtab = take(h->kind == B2R_KIND_IVF_PQ ? (size_t)pl.chunk * h->pq_m * 256 * 4 : 0);
   pl.total = off;
@@ -1050,10 +1070,17 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     if ((rc = launch_prep_queries(queries + (size_t)q0 * d, qc, qpad, d, normalize, q32, q16, h->scan_fp16 == 1, qnorm,
                                   stream)))
       return rc;
-    // coarse quantiser: exact top-nprobe centroids, best first (faiss quantizer->search)
-    if ((rc = flat_search(h->quantizer, qc, q32, 0, np, cdist, coarse, nullptr, nullptr, nullptr, ws + pl.off_qws,
-                          pl.qws_bytes, stream)))
-      return rc;
+    // coarse quantiser: exact top-nprobe centroids, best first (faiss quantizer->search).  Dense path: the
+    // candidate threshold is the exact k-th scan score minus the rescore margin, so the probed list set cannot
+    // depend on a sampled threshold; what the flat search still flags (candidate overflow among near-ties) is
+    // OR-ed into the caller's status words below instead of being dropped.
+    int32_t* cstatus = reinterpret_cast<int32_t*>(ws + pl.off_cstatus);
+    {
+      ForcePath dense(h->quantizer, 1);
+      rc = flat_search(h->quantizer, qc, q32, 0, np, cdist, coarse, status ? cstatus : nullptr, nullptr, nullptr,
+                       ws + pl.off_qws, pl.qws_bytes, stream);
+    }
+    if (rc) return rc;
     if (h->ntotal == 0) {
       if ((rc = launch_fill_f32(D + (size_t)q0 * k, (int64_t)qc * k, -3.4028234663852886e38f, stream))) return rc;
       B2R_CUDA(cudaMemsetAsync(I + (size_t)q0 * k, 0xFF, (size_t)qc * k * 8, stream));
@@ -1127,6 +1154,10 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     sel.tau_retry = nullptr;
     sel.scanned = row_len;
     if ((rc = launch_select_rescore(sel, stream))) return rc;
+    if (status) {
+      or_status_kernel<<<(unsigned)ceil_div(qc, 256), 256, 0, stream>>>(status + q0, cstatus, qc);
+      B2R_CHECK_LAUNCH("or_status_kernel");
+    }
   }
   return B2R_OK;
 }

@@ -75,7 +75,15 @@ struct FtParams {
   int KC1;                // layer-1 K chunks (K1p / 64)
   int N1p, N2p, N3p;      // padded widths (multiples of 128; <= 512 / 256 / 256)
   int32_t* err_flag;
+  long long* trace;       // debug: [4 CTAs][8 tiles][64 events] clock64 stamps (null in production)
 };
+
+// debug timeline (set_param trace_ptr): event `slot` of local tile `it`, first 4 CTAs only
+#define FT_TRACE(it_, slot_)                                                                     \
+  do {                                                                                           \
+    if (p.trace && blockIdx.x < 4 && (it_) < 8 && lane == 0)                                     \
+      p.trace[((size_t)blockIdx.x * 8 + (it_)) * 64 + (slot_)] = clock64();                      \
+  } while (0)
 
 __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
   float4 v;
@@ -86,6 +94,19 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
 }
 // fp32 pair -> packed 16-bit pair.  fp16: round-to-nearest, saturating to +-65504 (the caller tracks |v| and
 // raises kTowerErrSaturate); bf16: round-to-nearest-even, fp32 range.
+// ReLU fused into the conversion (cvt.rn.relu): max(x, 0) -> 16-bit pair
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
+  uint32_t r;
+  if (BF16) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
 template <bool BF16>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   uint32_t r;
@@ -224,11 +245,14 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const uint32_t tpar = it & 1;
       // the previous tile's epilogues 2 and 3 must have drained their accumulators before GEMM1 overwrites them
+      FT_TRACE(it, 0);
       mbar_wait(bar(FtBars::tmem_free), tpar ^ 1, 23);
       tc_fence_after_sync();
+      FT_TRACE(it, 1);
       for (int kc = 0; kc < KC1; ++kc) {
         mbar_wait(bar(FtBars::a_full + as), aph, 24);
         tc_fence_after_sync();
+        if (kc < 8) FT_TRACE(it, 2 + kc);
         chunk(descA + (uint64_t)((as * kSlot) >> 4), NT1, 0u, kc == 0);
         if (elect_one()) umma_commit(bar(FtBars::a_empty + as));
         __syncwarp();
@@ -236,9 +260,11 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       }
       if (elect_one()) umma_commit(bar(FtBars::acc_full + 0));
       __syncwarp();
+      FT_TRACE(it, 10);
       // GEMM2 accumulates into columns [0, N2p): those must have been drained by epilogue 1, i.e. the H1
       // chunks that came out of them are complete
       for (int kc = 0; kc < KC3 && kc < KC2; ++kc) mbar_wait(bar(FtBars::h1_ready + kc), tpar, 25);
+      FT_TRACE(it, 11);
       for (int kc = 0; kc < KC2; ++kc) {
         mbar_wait(bar(FtBars::h1_ready + kc), tpar, 26);
         tc_fence_after_sync();
@@ -246,6 +272,7 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       }
       if (elect_one()) umma_commit(bar(FtBars::acc_full + 1));
       __syncwarp();
+      FT_TRACE(it, 12);
       for (int kc = 0; kc < KC3; ++kc) {
         mbar_wait(bar(FtBars::h2_ready + kc), tpar, 27);
         tc_fence_after_sync();
@@ -253,6 +280,7 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       }
       if (elect_one()) umma_commit(bar(FtBars::acc_full + 2));
       __syncwarp();
+      FT_TRACE(it, 13);
     }
   } else if (warp == 3) {
     // ============================================================ L2 prefetch of the NEXT tile's ids (contiguous block)
@@ -269,8 +297,6 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
           for (int64_t o = (int64_t)lane * 128; o < nb; o += 32 * 128) prefetch_l2(n0 + o);
         }
       }
-      // pace: one tile's worth of prefetch per tile of work (wait for this tile's GEMM1 to finish)
-      // -- not needed for correctness; the loop is short, so simply run ahead.
     }
   } else if (warp >= kFtGatherWarp0) {
     // ============================================================ gather: build the layer-1 A operand chunk by chunk
@@ -282,9 +308,11 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     uint32_t ph = 0;
     bool bad = false;
     float amax = 0.f;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    uint32_t git = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++git) {
       const int64_t row0 = (int64_t)tile * 128;
       for (int kc = 0; kc < KC1; ++kc) {
+        if (warp == kFtGatherWarp0 && kc < 8) FT_TRACE(git, 16 + kc);
         const int w4 = kc * 16 + piece;
         float4 v[8];
         if (w4 < FE4) {
@@ -334,11 +362,12 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(FtBars::a_full + slot));
+        if (warp == kFtGatherWarp0 && kc < 8) FT_TRACE(git, 24 + kc);
         if (++slot == kNA) { slot = 0; ph ^= 1; }
       }
     }
     int flags = bad ? kTowerErrIndex : 0;
-    if (!BF16 && !(amax <= 65504.f)) flags |= kTowerErrSaturate;   // also catches NaN / inf inputs
+    if (!BF16 && !(amax <= 65504.f)) flags |= kTowerErrSaturate;   // also catches +-inf inputs
     if (flags && p.err_flag) atomicOr(p.err_flag, flags);
   } else if (warp >= kFtEpiWarp0) {
     // ============================================================ epilogues
@@ -349,7 +378,7 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t stage = sH + 65536u + (uint32_t)e * 8192u;  // 2 x 4 KB output staging (H chunks 4..7)
     float* ssx = reinterpret_cast<float*>(smem);               // [8][32] partial sums of squares (H chunk 0, free in epilogue 3)
-    float amax = 0.f;
+    uint32_t hmax = 0u;      // running max of the packed fp16 activations (>= 0 after ReLU): 0x7BFF = saturated
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const uint32_t tpar = it & 1;
@@ -360,18 +389,19 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
         const int boff = layer == 0 ? 0 : p.N1p;
         mbar_wait(bar(FtBars::acc_full + layer), tpar, 29);
         tc_fence_after_sync();
+        if (e == 0) FT_TRACE(it, 32 + layer * 2);
 #pragma unroll 1
         for (int kc = 0; kc < KC; ++kc) {
           const int c = kc * 2 + half;     // 32-column chunk
           tmem_ld_32x32(tlane + (uint32_t)(c * 32), r);
           tmem_ld_wait_dep(r);
           uint32_t pk[16];
+          const float2* b2 = reinterpret_cast<const float2*>(bias.v + boff + c * 32);
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float a = fmaxf(__uint_as_float(r[i]) + bias.v[boff + c * 32 + i], 0.f);
-            const float b = fmaxf(__uint_as_float(r[i + 1]) + bias.v[boff + c * 32 + i + 1], 0.f);
-            if (!BF16) amax = fmaxf(amax, fmaxf(a, b));
-            pk[i >> 1] = pack2<BF16>(a, b);
+          for (int i = 0; i < 16; ++i) {
+            const float2 bb = b2[i];
+            pk[i] = pack2_relu<BF16>(__uint_as_float(r[2 * i]) + bb.x, __uint_as_float(r[2 * i + 1]) + bb.y);
+            if (!BF16) hmax = hmax2_u32(hmax, pk[i]);
           }
           const uint32_t dst = sH + (uint32_t)(kc * kSlot);
 #pragma unroll
@@ -382,10 +412,12 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(bar((layer == 0 ? FtBars::h1_ready : FtBars::h2_ready) + kc));
         }
+        if (e == 0) FT_TRACE(it, 33 + layer * 2);
       }
       // ---- output layer: bias, L2 norm over the whole row (two warps share a row quarter), fp32, TMA store
       mbar_wait(bar(FtBars::acc_full + 2), tpar, 30);
       tc_fence_after_sync();
+      if (e == 0) FT_TRACE(it, 36);
       const int boff3 = p.N1p + p.N2p;
       float ss = 0.f;
 #pragma unroll 1
@@ -399,6 +431,7 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
           ss = fmaf(v, v, ss);
         }
       }
+      if (e == 0) FT_TRACE(it, 37);
       ssx[e * 32 + lane] = ss;
       asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");      // the two warps of this lane quarter
       const float other = ssx[(e ^ 4) * 32 + lane];
@@ -437,11 +470,15 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       }
       // the staging buffers and ssx live in the H region: every epilogue warp must be done with them (stores
       // have READ shared memory) before any warp starts writing the next tile's H1 there
+      if (e == 0) FT_TRACE(it, 38);
       if (lane == 0) bulk_wait_read<0>();
       __syncwarp();
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (e == 0) FT_TRACE(it, 39);
     }
-    if (!BF16 && !(amax <= 65504.f) && p.err_flag) atomicOr(p.err_flag, kTowerErrSaturate);
+    // a hidden activation that hit the fp16 ceiling (cvt.satfinite clamps to 65504 = 0x7BFF; NaN stays NaN = 0x7FFF)
+    if (!BF16 && ((hmax & 0xFFFFu) >= 0x7BFFu || (hmax >> 16) >= 0x7BFFu) && p.err_flag)
+      atomicOr(p.err_flag, kTowerErrSaturate);
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // global writes complete before exit
   }
   __syncwarp();
@@ -506,6 +543,7 @@ int launch_tower_fused(b2r_tower* t, const int64_t* cat, const float* num, int64
   p.N2p = t->np[1];
   p.N3p = t->np[2];
   p.err_flag = err_flag;
+  p.trace = reinterpret_cast<long long*>(t->trace_ptr);
   static bool configured[2][64] = {};
   int dev = 0;
   B2R_CUDA(cudaGetDevice(&dev));

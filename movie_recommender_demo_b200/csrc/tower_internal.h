@@ -16,6 +16,7 @@ struct b2r_tower {
   // the fp16 range).  Both weight copies are kept so the switch costs nothing at run time.
   int bf16 = 0;
   int force_path = 0;            // 0 auto, 1 layer-by-layer kernels, 2 fused kernel (tests)
+  uintptr_t trace_ptr = 0;       // debug: device buffer for the fused kernel's phase timeline (tests/prof_tower.py)
   __half* w[3] = {nullptr, nullptr, nullptr};          // [np[l], Kp[l]] fp16, zero padded
   __nv_bfloat16* wb[3] = {nullptr, nullptr, nullptr};  // the same weights in bf16
   float* b[3] = {nullptr, nullptr, nullptr};           // [np[l]]

@@ -544,6 +544,8 @@ int b2r_tower_set_param(b2r_tower* t, const char* name, double value) {
   if (n == "operand_dtype") {         // 0 fp16 | 1 bf16
     if (value != 0 && value != 1) return fail(B2R_EINVAL, "operand_dtype must be 0 (fp16) or 1 (bf16)");
     t->bf16 = (int)value;
+  } else if (n == "trace_ptr") {      // debug: device pointer (as a double; < 2^53) of a [4][8][64] int64 buffer, 0 = off
+    t->trace_ptr = (uintptr_t)value;
   } else if (n == "force_path") {     // 0 auto | 1 layer-by-layer | 2 fused
     if (value == 2 && !t->fused_ok) return fail(B2R_EUNSUPPORTED, "this tower's shape does not fit the fused kernel");
     t->force_path = (int)value;

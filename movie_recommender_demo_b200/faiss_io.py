@@ -332,6 +332,18 @@ def write_index(index, path: str) -> None:
         _w_index(f, describe(index))
 
 
+def _keep_fp16_scan_copy(index, rows) -> None:
+    """A file holds the rows `add` stored - for the reference's wrapper always L2-normalised (faiss_retrieval.py:115).
+    Re-adding them verbatim (normalize=False) must not silently demote the 16-bit scan copy from fp16 to bf16
+    (wider rescore windows, more candidates than the index that was saved): unit-norm rows keep fp16."""
+    x = np.asarray(rows, dtype=np.float32)
+    if x.size == 0:
+        return
+    n2 = np.einsum("ij,ij->i", x, x)
+    if np.all(np.abs(n2 - 1.0) < 1e-3):
+        index.set_param("scan_dtype", 1)
+
+
 def build(desc: Dict, device=None):
     """faiss-format description -> a device index of this package."""
     from .faiss_retrieval import IndexFlatIP, IndexHNSWFlat
@@ -343,6 +355,7 @@ def build(desc: Dict, device=None):
         index = IndexHNSWFlat(d, desc["M"], device=device)
         index.hnsw.efConstruction, index.hnsw.efSearch = desc["efConstruction"], desc["efSearch"]
         if desc["ntotal"]:
+            _keep_fp16_scan_copy(index, desc["xb"])
             index.add(desc["xb"], normalize=False)      # raises unless the stored rows have unit norm
         return index
     if kind == "Flat":
@@ -350,6 +363,7 @@ def build(desc: Dict, device=None):
             raise FaissFormatError("only inner-product flat indexes are on the hot path (IndexFlatIP)")
         index = IndexFlatIP(d, device=device)
         if desc["ntotal"]:
+            _keep_fp16_scan_copy(index, desc["xb"])
             index.add(desc["xb"], normalize=False)
         return index
     quant = desc["quantizer"]
@@ -374,7 +388,9 @@ def build(desc: Dict, device=None):
         if kind == "IVF":
             # rows are re-assigned by the imported centroids on add — identical to the file's lists
             # except on exact centroid ties (the same arg-max the file's writer ran)
-            index.add(payload.view(np.float32).reshape(desc["ntotal"], d), normalize=False)
+            rows = payload.view(np.float32).reshape(desc["ntotal"], d)
+            _keep_fp16_scan_copy(index, rows)
+            index.add(rows, normalize=False)
         else:
             index.add_codes(payload, lists)
     return index
@@ -389,6 +405,8 @@ def sniff(path: str) -> str:
     """'native' for this package's own container, 'faiss' for a faiss fourcc, else 'unknown'."""
     with open(path, "rb") as f:
         head = f.read(8)
+    if head == b"B2RIDX02":
+        return "native"        # b2r_index_save container (csrc/persist.cu)
     if head == b"B2RIDX01":
-        return "native"
+        return "native-py"     # round-1 pickled container, still readable
     return "faiss" if head[:4] in (b"IxFI", b"IxF2", b"IxFl", b"IwFl", b"IwPQ", b"IHNf") else "unknown"

@@ -701,6 +701,13 @@ class FAISSIndex:
         self._say(f"Index saved to {filepath}")
 
     def _save_native(self, filepath: str) -> None:
+        """`b2r_index_save` (csrc/persist.cu): the C-ABI container any host language can write and read."""
+        idx = self.index
+        torch = idx._torch
+        with torch.cuda.device(idx.device):
+            _lib.check(idx._lib.b2r_index_save(idx._h, os.fsencode(filepath), _stream_ptr(torch, idx.device)))
+
+    def _save_native_py(self, filepath: str) -> None:   # round-1 container (kept for its reader's test)
         state = self.index.state_dict() if hasattr(self.index, "state_dict") else {}
         n = self.index.ntotal
         if n and getattr(self.index, "stores_vectors", True):
@@ -738,6 +745,8 @@ class FAISSIndex:
             self._pq_m = getattr(index, "pq_m", self._pq_m)
         elif layout == "native":
             self._load_native(filepath)
+        elif layout == "native-py":
+            self._load_native_py(filepath)
         else:
             raise ValueError(f"{filepath}: neither a faiss index file (IxFI/IwFl/IwPQ/IHNf) nor a b200 native container")
         self.id_map = list(meta['id_map'])
@@ -747,6 +756,24 @@ class FAISSIndex:
         self._say(f"Index size: {self.index.ntotal}")
 
     def _load_native(self, filepath: str) -> None:
+        """`b2r_index_load`: the handle comes back fully built (quantisers, rows / codes, id map, scan format);
+        it is adopted by the faiss-shaped Python object of the type the metadata names."""
+        verbose, self.verbose = self.verbose, False
+        try:
+            self._create_index()          # right Python class / attributes for index_type; its empty handle is replaced
+        finally:
+            self.verbose = verbose
+        idx = self.index
+        torch = idx._torch
+        h = C.c_void_p()
+        with torch.cuda.device(idx.device):
+            _lib.check(idx._lib.b2r_index_load(C.byref(h), os.fsencode(filepath), idx.device.index,
+                                               _stream_ptr(torch, idx.device)))
+        idx._lib.b2r_index_destroy(idx._h)
+        idx._h = h
+        idx._graphs = {}
+
+    def _load_native_py(self, filepath: str) -> None:
         with open(filepath, "rb") as f:
             f.read(8)
             (blen,) = struct.unpack("<Q", f.read(8))

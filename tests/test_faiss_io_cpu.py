@@ -127,6 +127,8 @@ def test_reader_rejects_what_it_cannot_represent(tmp_path):
     p.write_bytes(good)
     assert fio.sniff(str(p)) == "faiss"
     p.write_bytes(b"B2RIDX01....")
-    assert fio.sniff(str(p)) == "native"
+    assert fio.sniff(str(p)) == "native-py"        # round-1 pickled container
+    p.write_bytes(b"B2RIDX02....")
+    assert fio.sniff(str(p)) == "native"           # b2r_index_save container (csrc/persist.cu)
     p.write_bytes(b"garbage!")
     assert fio.sniff(str(p)) == "unknown"

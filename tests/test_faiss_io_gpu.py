@@ -43,6 +43,9 @@ def test_round_trip_both_layouts(fr, tmp_path, kind, fourcc):
         h = fr.FAISSIndex(d, 'Flat')
         h.load(path)
         assert h.index_type == kind and h.index.ntotal == N and h.id_map == ad_ids
+        # a loaded index must search like the saved one: same 16-bit scan format (fp16 for normalised rows),
+        # hence the same rescore window and candidate target
+        assert h.index.get_param("scan_dtype") == g.index.get_param("scan_dtype")
         results[layout] = h.search(q, k=60)
         assert np.array_equal(results[layout][0], ids)
         if kind == "IVFPQ":      # codes + codebooks travel verbatim -> same ADC scores
@@ -119,3 +122,54 @@ def test_load_rejects_mismatched_metadata(fr, tmp_path):
     open(path, "wb").write(b"not an index")
     with pytest.raises(ValueError, match="neither a faiss index file"):
         fr.FAISSIndex(d, 'Flat').load(path)
+
+
+def test_native_container_through_the_c_abi_only(fr, built_lib, tmp_path):
+    """b2r_index_save / b2r_index_load called the way a non-Python host would (no wrapper, no metadata side-car):
+    the loaded handle returns the same labels / mapped ids / scores as the saved one, for all three kinds."""
+    import ctypes as C
+    import torch
+    from movie_recommender_demo_b200 import _lib
+    lib = built_lib
+    d, N, k = 128, 20000, 50
+    x = torch.from_numpy(_clustered(N, d, 40, seed=5)).cuda()
+    q = torch.from_numpy(_clustered(7, d, 40, seed=6)).cuda()
+    sp = int(torch.cuda.current_stream().cuda_stream)
+    for kind, nlist, pq_m, metric in ((0, 0, 0, 0), (1, 16, 0, 0), (2, 16, 16, 1)):
+        h = C.c_void_p()
+        _lib.check(lib.b2r_index_create(C.byref(h), kind, d, nlist, pq_m, 8 if pq_m else 0, metric, 0))
+        if kind:
+            _lib.check(lib.b2r_index_train(h, N, x.data_ptr(), 1234, sp))
+        _lib.check(lib.b2r_index_add(h, N, x.data_ptr(), 1, sp))
+        ids = (torch.arange(N, device="cuda", dtype=torch.int64) * 5 + 11)
+        _lib.check(lib.b2r_index_set_ids(h, N, ids.data_ptr(), sp))
+
+        def search(handle):
+            D = torch.empty((7, k), dtype=torch.float32, device="cuda")
+            I = torch.empty((7, k), dtype=torch.int64, device="cuda")
+            st = torch.zeros(7, dtype=torch.int32, device="cuda")
+            need = int(lib.b2r_index_search_workspace(handle, 7, k, 4))
+            ws = torch.empty(max(need, 256), dtype=torch.uint8, device="cuda")
+            _lib.check(lib.b2r_index_search(handle, 7, q.data_ptr(), 1, k, 4, D.data_ptr(), I.data_ptr(), st.data_ptr(),
+                                            None, None, ws.data_ptr(), ws.numel(), sp))
+            torch.cuda.synchronize()
+            return D.cpu().numpy(), I.cpu().numpy(), st.cpu().numpy()
+
+        D0, I0, st0 = search(h)
+        path = str(tmp_path / f"kind{kind}.b2r").encode()
+        _lib.check(lib.b2r_index_save(h, path, sp))
+        assert open(path, "rb").read(8) == b"B2RIDX02"
+        h2 = C.c_void_p()
+        _lib.check(lib.b2r_index_load(C.byref(h2), path, 0, sp))
+        assert lib.b2r_index_ntotal(h2) == N and lib.b2r_index_is_trained(h2) == 1
+        assert lib.b2r_index_get_param(h2, b"scan_dtype") == lib.b2r_index_get_param(h, b"scan_dtype")
+        D1, I1, st1 = search(h2)
+        assert np.array_equal(I0, I1) and (I0 % 5 == 1).all()
+        assert np.array_equal(D0, D1) if kind != 2 else np.allclose(D0, D1, rtol=1e-6, atol=1e-6)
+        assert (st0 == 0).all() and (st1 == 0).all()
+        lib.b2r_index_destroy(h)
+        lib.b2r_index_destroy(h2)
+    bad = tmp_path / "bad.b2r"
+    bad.write_bytes(b"not an index")
+    h3 = C.c_void_p()
+    assert lib.b2r_index_load(C.byref(h3), str(bad).encode(), 0, sp) != 0 and not h3.value
