@@ -300,71 +300,90 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     }
   } else if (warp >= kFtGatherWarp0) {
     // ============================================================ gather: build the layer-1 A operand chunk by chunk
+    // A thread owns one 4-float piece (column group) of the chunk for 8 rows: 8 ids -> 8 x 16-byte row loads.
+    // The table rows are RANDOM 64-byte reads over 16.6 GB (every access misses the TLB and DRAM: ~3.5k cycles in
+    // the phase trace) and the ids are a second DRAM-latency load in front of them, so the ids (and the table
+    // pointer) of chunk n+1 are fetched while the row loads of chunk n are in flight: one exposed latency per
+    // chunk instead of two.
     const int t = (warp - kFtGatherWarp0) * 32 + lane;   // 0..255
     const int piece = t & 15;                             // 4-float piece of the 64-column chunk
     const int rsub = t >> 4;                              // rows rsub, rsub + 16, ...
     const int FE4 = p.F * p.E4;
+    const int my_tiles = tiles > (int)blockIdx.x ? (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int items = my_tiles * KC1;                     // (tile, chunk) pairs this CTA gathers, in order
     int slot = 0;
     uint32_t ph = 0;
     bool bad = false;
     float amax = 0.f;
-    uint32_t git = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++git) {
-      const int64_t row0 = (int64_t)tile * 128;
-      for (int kc = 0; kc < KC1; ++kc) {
-        if (warp == kFtGatherWarp0 && kc < 8) FT_TRACE(git, 16 + kc);
-        const int w4 = kc * 16 + piece;
-        float4 v[8];
-        if (w4 < FE4) {
-          const int f = w4 / p.E4, part = w4 - f * p.E4;
-          const float4* tab = reinterpret_cast<const float4*>(p.tables[f]) + part;
-          const int64_t card = __ldg(p.cards + f);
-          int64_t idx[8];
+    // what a thread needs to know to issue the row loads of item n (tile n / KC1, chunk n % KC1)
+    struct Ids {
+      int64_t idx[8];      // table row per owned sample row; -1: row beyond the batch (or not an embedding piece)
+      const float4* tab;   // table base + this thread's 16-byte part
+      int64_t card;
+    };
+    auto load_ids = [&](int n, Ids& o) {
+      const int w4 = (n % KC1) * 16 + piece;
+      const bool emb = n < items && w4 < FE4;
+      const int f = emb ? w4 / p.E4 : 0;
+      o.tab = reinterpret_cast<const float4*>(p.tables[f]) + (emb ? w4 - f * p.E4 : 0);
+      o.card = __ldg(p.cards + f);
+      const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)(n / KC1) * gridDim.x) * 128;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int64_t grow = row0 + i * 16 + rsub;
-            idx[i] = grow < p.B ? __ldg(p.cat + grow * p.F + f) : -1;
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int64_t grow = row0 + i * 16 + rsub;
-            int64_t r = idx[i];
-            if (grow < p.B) {
-              if (r < 0 || r >= card) { bad = true; r = 0; }
-              v[i] = ldg_nc_f4(tab + r * p.E4);
-            } else {
-              v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-        } else {
-          const int c0 = (w4 - FE4) * 4;   // first numerical column of this piece
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int64_t grow = row0 + i * 16 + rsub;
-            float e[4] = {0.f, 0.f, 0.f, 0.f};
-            if (grow < p.B && p.num) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (c0 + j < p.nnum) e[j] = __ldg(p.num + grow * p.nnum + c0 + j);
-            }
-            v[i] = make_float4(e[0], e[1], e[2], e[3]);
-          }
-        }
-        mbar_wait(bar(FtBars::a_empty + slot), ph ^ 1, 28);
-        const uint32_t dst = sA + (uint32_t)(slot * kSlot);
+      for (int i = 0; i < 8; ++i) {
+        const int64_t grow = row0 + i * 16 + rsub;
+        o.idx[i] = (emb && grow < p.B) ? __ldg(p.cat + grow * p.F + f) : -1;
+      }
+    };
+    Ids cur;
+    load_ids(0, cur);
+    for (int n = 0; n < items; ++n) {
+      const int kc = n % KC1;
+      const uint32_t git = (uint32_t)(n / KC1);
+      const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)git * gridDim.x) * 128;
+      if (warp == kFtGatherWarp0 && kc < 8) FT_TRACE(git, 16 + kc);
+      const int w4 = kc * 16 + piece;
+      float4 v[8];
+      if (w4 < FE4) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int r = i * 16 + rsub;
-          if (!BF16) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
-          st_shared_v2(dst + sw128_off(r, piece >> 1) + (uint32_t)((piece & 1) * 8), pack2<BF16>(v[i].x, v[i].y),
-                       pack2<BF16>(v[i].z, v[i].w));
+          const int64_t grow = row0 + i * 16 + rsub;
+          int64_t r = cur.idx[i];
+          if (grow < p.B) {
+            if (r < 0 || r >= cur.card) { bad = true; r = 0; }
+            v[i] = ldg_nc_f4(cur.tab + r * p.E4);
+          } else {
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(FtBars::a_full + slot));
-        if (warp == kFtGatherWarp0 && kc < 8) FT_TRACE(git, 24 + kc);
-        if (++slot == kNA) { slot = 0; ph ^= 1; }
+      } else {
+        const int c0 = (w4 - FE4) * 4;   // first numerical column of this piece
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t grow = row0 + i * 16 + rsub;
+          float e[4] = {0.f, 0.f, 0.f, 0.f};
+          if (grow < p.B && p.num) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (c0 + j < p.nnum) e[j] = __ldg(p.num + grow * p.nnum + c0 + j);
+          }
+          v[i] = make_float4(e[0], e[1], e[2], e[3]);
+        }
       }
+      load_ids(n + 1, cur);                               // next chunk's ids ride behind this chunk's row loads
+      mbar_wait(bar(FtBars::a_empty + slot), ph ^ 1, 28);
+      const uint32_t dst = sA + (uint32_t)(slot * kSlot);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 16 + rsub;
+        if (!BF16) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+        st_shared_v2(dst + sw128_off(r, piece >> 1) + (uint32_t)((piece & 1) * 8), pack2<BF16>(v[i].x, v[i].y),
+                     pack2<BF16>(v[i].z, v[i].w));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(FtBars::a_full + slot));
+      if (warp == kFtGatherWarp0 && kc < 8) FT_TRACE(git, 24 + kc);
+      if (++slot == kNA) { slot = 0; ph ^= 1; }
     }
     int flags = bad ? kTowerErrIndex : 0;
     if (!BF16 && !(amax <= 65504.f)) flags |= kTowerErrSaturate;   // also catches +-inf inputs

@@ -32,19 +32,62 @@ for c in range(sh.lo // CHUNK, (sh.hi - 1) // CHUNK + 1):
     sh.add_local(rows[max(sh.lo, c * CHUNK) - c * CHUNK: min(sh.hi, (c + 1) * CHUNK) - c * CHUNK])
 gq = torch.Generator(device=dev).manual_seed(9)
 q = torch.randn((Q, D), generator=gq, device=dev)
-Dm, Im, st = sh.search_device(q, K)
-torch.cuda.synchronize()
+QB = 1024
+qb = torch.randn((QB, D), generator=gq, device=dev)
 ok = True
+full = None
 if rank == 0:
     full = IndexFlatIP(D, device=local)
     for c in range((N + CHUNK - 1) // CHUNK):
         full.add(chunk(c)[: min(CHUNK, N - c * CHUNK)], normalize=True)
-    Df, If, stf, _ = full.search_device(q, K, normalize=True)
-    same_ids = torch.equal(Im, If)
-    same_d = torch.equal(Dm, Df)
-    ok = same_ids and same_d and int((st != 0).sum()) == 0
-    print(f"multi_gpu_check world={world}: ids identical={same_ids} scores identical={same_d} "
-          f"status_nonzero={int((st != 0).sum())} -> {'PASS' if ok else 'FAIL'}")
+
+
+def report(tag, Dm, Im, st, queries):
+    """every rank holds the merged answer; rank 0 compares it with the unsharded search"""
+    global ok
+    torch.cuda.synchronize()
+    ranks_agree = True
+    for t in (Dm, Im):
+        ref = t.clone()
+        dist.broadcast(ref, src=0)
+        ranks_agree = ranks_agree and torch.equal(ref, t)
+    flag = torch.tensor([int(ranks_agree)], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        Df, If, stf, _ = full.search_device(queries, K, normalize=True)
+        same_ids, same_d = torch.equal(Im, If), torch.equal(Dm, Df)
+        good = same_ids and same_d and int((st != 0).sum()) == 0 and bool(flag.item())
+        ok = ok and good
+        print(f"multi_gpu_check world={world} {tag}: ids identical={same_ids} scores identical={same_d} "
+              f"status_nonzero={int((st != 0).sum())} all ranks hold the same answer={bool(flag.item())} "
+              f"-> {'PASS' if good else 'FAIL'}")
+
+
+from movie_recommender_demo_b200.sharded import exchange_mode  # noqa: E402
+
+# 1) small batch: packed all-gather exchange, replayed as a CUDA graph (local search + pack + NCCL + merge)
+Dm, Im, st = sh.search_device(q, K)
+report(f"flat Q={Q} [{exchange_mode(Q, world)} exchange, graph replay={bool(sh._graphs and any(sh._graphs.values()))}]",
+       Dm, Im, st, q)
+Dm2, Im2, st2 = sh.search_device(q, K)          # second replay of the same graph: static buffers, same answer
+report(f"flat Q={Q} [second replay]", Dm2, Im2, st2, q)
+os.environ["B2R_NO_GRAPHS"] = "1"
+Dm, Im, st = sh.search_device(q, K)             # the same exchange launched eagerly
+report(f"flat Q={Q} [{exchange_mode(Q, world)} exchange, eager]", Dm, Im, st, q)
+del os.environ["B2R_NO_GRAPHS"]
+# 2) large batch: all-to-all by query slice + merge of one slice per rank + all-gather of the merged slices
+Dm, Im, st = sh.search_device(qb, K)
+report(f"flat Q={QB} [{exchange_mode(QB, world)} exchange]", Dm, Im, st, qb)
+# 3) host-result search with FORCED threshold misses: flagged queries are re-run collectively
+sh.local.set_param("cand_factor", 1.0)
+sh._graphs = {}
+Dh, Ih = sh.search(qb.cpu().numpy(), K)
+sh.local.set_param("cand_factor", 2.5)
+sh._graphs = {}
+retried = torch.tensor([sh.last_retries], device=dev)
+dist.all_reduce(retried, op=dist.ReduceOp.MAX)
+report(f"flat Q={QB} host search, forced retries (rounds={int(retried.item())})", torch.from_numpy(Dh).to(dev),
+       torch.from_numpy(Ih).to(dev), torch.from_numpy(sh.last_status).to(dev), qb)
 
 # ---- IVF-Flat and IVF-PQ: replicated quantisers, row-sharded lists (SURVEY.md §8e) ----------------
 from movie_recommender_demo_b200 import ivf  # noqa: E402

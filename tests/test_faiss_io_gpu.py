@@ -45,7 +45,8 @@ def test_round_trip_both_layouts(fr, tmp_path, kind, fourcc):
         assert h.index_type == kind and h.index.ntotal == N and h.id_map == ad_ids
         # a loaded index must search like the saved one: same 16-bit scan format (fp16 for normalised rows),
         # hence the same rescore window and candidate target
-        assert h.index.get_param("scan_dtype") == g.index.get_param("scan_dtype")
+        if kind != "IVFPQ":      # IVF-PQ stores codes only: no 16-bit scan copy
+            assert h.index.get_param("scan_dtype") == g.index.get_param("scan_dtype")
         results[layout] = h.search(q, k=60)
         assert np.array_equal(results[layout][0], ids)
         if kind == "IVFPQ":      # codes + codebooks travel verbatim -> same ADC scores
@@ -162,7 +163,8 @@ def test_native_container_through_the_c_abi_only(fr, built_lib, tmp_path):
         h2 = C.c_void_p()
         _lib.check(lib.b2r_index_load(C.byref(h2), path, 0, sp))
         assert lib.b2r_index_ntotal(h2) == N and lib.b2r_index_is_trained(h2) == 1
-        assert lib.b2r_index_get_param(h2, b"scan_dtype") == lib.b2r_index_get_param(h, b"scan_dtype")
+        if kind != 2:      # IVF-PQ stores codes only: no 16-bit scan copy whose format could change
+            assert lib.b2r_index_get_param(h2, b"scan_dtype") == lib.b2r_index_get_param(h, b"scan_dtype")
         D1, I1, st1 = search(h2)
         assert np.array_equal(I0, I1) and (I0 % 5 == 1).all()
         assert np.array_equal(D0, D1) if kind != 2 else np.allclose(D0, D1, rtol=1e-6, atol=1e-6)

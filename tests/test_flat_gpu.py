@@ -542,6 +542,7 @@ def test_packed_exchange_kernels_match_unsharded(fr, built_lib, P, Q, k, q_rows)
     if P * k <= 8192:
         D2 = torch.empty((Q, k), dtype=torch.float32, device="cuda")
         I2 = torch.empty((Q, k), dtype=torch.int64, device="cuda")
-        _lib.check(built_lib.b2r_topk_merge(P, Q, k, torch.stack(Ds).contiguous().data_ptr(),
-                                            torch.stack(Is).contiguous().data_ptr(), D2.data_ptr(), I2.data_ptr(), 1, sp))
+        D_all, I_all = torch.stack(Ds).contiguous(), torch.stack(Is).contiguous()      # kept alive across the launch
+        _lib.check(built_lib.b2r_topk_merge(P, Q, k, D_all.data_ptr(), I_all.data_ptr(), D2.data_ptr(), I2.data_ptr(), 1, sp))
+        torch.cuda.synchronize()
         assert torch.equal(I2, I_out[:Q]) and torch.equal(D2, D_out[:Q])
