@@ -739,8 +739,18 @@ def run_b200(args):
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
+        # captured graphs hold NCCL kernels: release them before the communicator goes away, and never let a
+        # teardown problem turn a finished measurement into a hung job
+        sharded.release_graphs()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        import threading
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(timeout=30)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

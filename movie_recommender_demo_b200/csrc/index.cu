@@ -55,6 +55,28 @@ struct Plan {
          off_cidx = 0, off_aux = 0, total = 0;
 };
 
+// Launch geometry of the filter scan for a chunk of q queries over `tiles` 128-row corpus tiles.
+// pair: CTA-pair kernel (scan_pair.cu) — query groups of 256, 256-row pair tiles, units spread over num_sms / 2
+// clusters, 4 candidate segments per split; else the one-CTA kernel of scan_tc.cu (MQ, 1 or 2 segments per split).
+struct ScanGeom {
+  int MQ = 1, QG = 1, splits = 1, seg_per_split = 1, qpad = 0;
+  bool pair = false;
+};
+ScanGeom scan_geometry(const b2r_index* h, int q, int tiles, bool filter) {
+  ScanGeom g;
+  plan_scan(q, tiles, h->num_sms, &g.MQ, &g.QG, &g.splits);
+  g.qpad = g.QG * g.MQ * kQBlock;
+  g.pair = filter && h->pair_scan && g.MQ == 2 && h->num_sms >= 2 && tiles >= 2;
+  if (g.pair) {
+    int mq, qg;
+    plan_scan(q, (int)ceil_div(tiles, 2), h->num_sms / 2, &mq, &qg, &g.splits);   // qg == g.QG: groups of 256 queries
+    g.seg_per_split = 4;
+  } else {
+    g.seg_per_split = (g.MQ == 1 || h->epi_warps == 16) ? 2 : 1;
+  }
+  return g;
+}
+
 Plan make_plan(const b2r_index* h, int q, int k, bool have_tau) {
   Plan pl;
   const int64_t N = h->ntotal;
@@ -84,16 +106,22 @@ Plan make_plan(const b2r_index* h, int q, int k, bool have_tau) {
     if (chunk > 8192) chunk = 8192;
   }
   pl.chunk = chunk;
-  plan_scan(chunk, pl.tiles, h->num_sms, &pl.MQ, &pl.QG, &pl.splits);
-  pl.qpad = pl.QG * pl.MQ * kQBlock;
+  const ScanGeom geo = scan_geometry(h, chunk, pl.tiles, !pl.dense);
+  pl.MQ = geo.MQ;
+  pl.QG = geo.QG;
+  pl.splits = geo.splits;
+  pl.qpad = geo.qpad;
   if (pl.dense) {
     pl.nseg = 1;
     pl.cap_seg = cap;
   } else {
-    // filter path: one private segment per (query, corpus split[, column half]); sized for the
-    // worst chunk geometry (a smaller last chunk may pick MQ = 1 -> two segments per split)
-    pl.nseg = pl.splits * 2;
-    int per = (int)ceil_div(4 * (int64_t)ct, pl.splits);  // 4x the mean entries per segment
+    // filter path: one private segment per (query, corpus split, column part); sized for the worst chunk
+    // geometry (a smaller last chunk may pick another kernel with fewer segments per split: each of its
+    // segments then holds more entries, so the slot count is sized for TWO segments per split)
+    const int sps = geo.seg_per_split < 2 ? 2 : geo.seg_per_split;
+    pl.nseg = pl.splits * sps;
+    int per = (int)ceil_div(4 * (int64_t)ct, pl.splits);  // 8x the mean entries of a half-split segment
+    if (sps == 4) per = (int)ceil_div(3 * (int64_t)ct, pl.splits);  // 12x the mean of a quarter-split segment
     int cs = 32;
     while (cs < per) cs <<= 1;
     if (cs > cap) cs = cap;
@@ -182,9 +210,10 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
   float* aux = reinterpret_cast<float*>(ws + pl.off_aux);
   int rc;
   // plan for THIS chunk size (the last chunk may be smaller)
-  int MQ, QG, splits;
-  plan_scan(q, pl.tiles, h->num_sms, &MQ, &QG, &splits);
-  const int qpad = QG * MQ * kQBlock;  // <= pl.qpad
+  const ScanGeom geo = scan_geometry(h, q, pl.tiles, !pl.dense);
+  const int MQ = geo.MQ, QG = geo.QG;
+  int splits = geo.splits;
+  const int qpad = geo.qpad;  // <= pl.qpad
   const int fp16 = h->scan_fp16 == 1;
   const float eps = (float)(fp16 ? h->eps_fp16 : h->eps);
   // tau[0, qpad) = +inf is written by the same launch (padding queries must never produce candidates)
@@ -209,8 +238,14 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
   sp.splits = splits;
   sp.cand_count = count;
   sp.cand = cand;
+  sp.early_release = h->early_release;
   const int epi_warps = (MQ == 2 && h->epi_warps == 16) ? 16 : 8;
-  sp.nseg = splits * ((MQ == 1 || epi_warps == 16) ? 2 : 1);
+  // the chunk's segments must fit the planned buffer: nseg <= pl.nseg (cap_seg is the plan's)
+  if (!pl.dense) {
+    while (splits > 1 && splits * geo.seg_per_split > pl.nseg) --splits;
+    sp.splits = splits;
+  }
+  sp.nseg = splits * geo.seg_per_split;
   sp.cap_seg = pl.cap_seg;
   int sel_nseg = sp.nseg, sel_cap_seg = pl.cap_seg;
 
@@ -244,7 +279,14 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
   if (tau_in || !pl.dense) {
     const bool prof = h->profile && h->prof_used + 2 <= h->prof_ev.size();
     if (prof) cudaEventRecord(h->prof_ev[h->prof_used], stream);
-    if ((rc = launch_scan(SCAN_FILTER, MQ, tmQ, h->tmX, sp, h->num_sms, stream, epi_warps, h->walk))) return rc;
+    if (geo.pair) {
+      ScanParams pp = sp;            // pair tiles of 256 rows, UMMA M = N = 256
+      pp.tile_count = (int)ceil_div(pl.tiles, 2);
+      pp.idesc = scan_idesc_pair(fp16);
+      if ((rc = launch_scan_pair(tmQ, h->tmX, pp, h->num_sms, stream, h->walk))) return rc;
+    } else if ((rc = launch_scan(SCAN_FILTER, MQ, tmQ, h->tmX, sp, h->num_sms, stream, epi_warps, h->walk))) {
+      return rc;
+    }
     if (prof) {
       cudaEventRecord(h->prof_ev[h->prof_used + 1], stream);
       h->prof_used += 2;
@@ -523,6 +565,8 @@ int b2r_index_set_param(b2r_index* h, const char* name, double value) {
     if (value != 8 && value != 16) return fail(B2R_EINVAL, "epi_warps must be 8 or 16");
     h->epi_warps = (int)value;
   }
+  else if (n == "pair_scan") h->pair_scan = value != 0;
+  else if (n == "early_release") h->early_release = value != 0;
   else if (n == "walk") h->walk = value != 0;
   else if (n == "rescore") h->rescore = value != 0;
   else if (n == "force_path") h->force_path = (int)value;
@@ -554,6 +598,8 @@ double b2r_index_get_param(const b2r_index* h, const char* name) {
   if (n == "cand_factor") return h->cand_factor;
   if (n == "cand_cap") return h->cand_cap;
   if (n == "epi_warps") return h->epi_warps;
+  if (n == "pair_scan") return h->pair_scan;
+  if (n == "early_release") return h->early_release;
   if (n == "walk") return h->walk;
   if (n == "rescore") return h->rescore;
   if (n == "force_path") return h->force_path;

@@ -107,6 +107,11 @@ uint32_t scan_idesc(int fp16) {
   const uint32_t fmt = fp16 ? 0u : ((1u << 7) | (1u << 10));
   return (1u << 4) | fmt | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 }
+uint32_t scan_idesc_pair(int fp16) {
+  // the same descriptor with M = 256 (both CTAs of a pair, 128 rows each) and N = 256
+  const uint32_t fmt = fp16 ? 0u : ((1u << 7) | (1u << 10));
+  return (1u << 4) | fmt | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+}
 
 int launch_reencode(const float* x32, int64_t n, int d, __nv_bfloat16* out16, int fp16, cudaStream_t stream) {
   if (n <= 0) return B2R_OK;

@@ -72,6 +72,7 @@ struct ScanParams {
   uint2* cand;           // [Qpad, nseg, cap_seg] (score bits, local row index)
   int nseg;              // splits * (MQ == 1 ? 2 : 1)
   int cap_seg;
+  int early_release;     // FILTER, 2 chunks per warp: free the accumulator buffer before the scores are examined
   // GMAX
   float* gmax;           // [Qpad, gstride]; entry (q, j*4 + chunk)
   int gstride;
@@ -88,6 +89,11 @@ int launch_scan(int mode, int MQ, const CUtensorMap& tmQ, const CUtensorMap& tmX
                 const ScanParams& p, int num_sms, cudaStream_t stream, int epi_warps = 8, int walk = 0);
 // picks (MQ, splits) for a (Q, tiles) problem
 void plan_scan(int Q, int tile_count, int num_sms, int* MQ, int* QG, int* splits);
+// FILTER scan on CTA pairs (scan_pair.cu, tcgen05 cta_group::2): p.QG = groups of 256 queries, p.tile_count =
+// 256-row pair tiles, p.nseg = 4 * p.splits, p.idesc = scan_idesc_pair()
+int launch_scan_pair(const CUtensorMap& tmQ, const CUtensorMap& tmX, const ScanParams& p, int num_sms,
+                     cudaStream_t stream, int walk);
+uint32_t scan_idesc_pair(int fp16);
 
 // --------------------------------------------------------- ingest / queries ---
 // rows fp32 [n,d] -> (optional L2 normalise) -> fp32 master + bf16 copy; updates *maxnorm
@@ -161,6 +167,9 @@ struct b2r_index {
   int scan_fp16 = -1;       // current format of x16 (-1: nothing stored yet)
   double cand_factor_fp16 = 2.5;
   int walk = 1;                  // FILTER hit walk: 1 = only the passing 3-element sub-groups (2-5 % faster), 0 = all 8
+  int early_release = 0;         // filter epilogue: release the TMEM buffer before the scores are examined (A/B: no gain)
+  int pair_scan = 0;             // 1: FILTER scan of batches > 128 on CTA pairs (cta_group::2, scan_pair.cu).  Correct
+                                 // (same answers) but measured 5-10 % SLOWER than the one-CTA kernel: off by default
   int epi_warps = 16;            // epilogue warps of the MQ = 2 filter scan (8 | 16); 16 measured 8-9 % faster
   double cand_factor = 4.0;
   int cand_cap = 4096;

@@ -297,6 +297,29 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           // sectors per store instruction.  Keep the tile's maxima in registers and store them 8 or 16
           // bytes at a time (4x fewer store sectors than one 4-byte store per chunk).
           float gm0 = 0.f, gm1 = 0.f, gm_prev0 = 0.f, gm_prev1 = 0.f;
+          if (MODE == SCAN_FILTER && NCH == 2 && p.early_release) {
+            // both chunks to registers, release the accumulator buffer, THEN look at the scores: the MMA warp
+            // gets the buffer back one chunk-processing time (~800 cycles) earlier
+            tmem_ld_32x32(taddr, r0);
+            tmem_ld_32x32(taddr + 32, r1);
+            tmem_ld_wait_dep(r0);
+            tmem_ld_wait_dep(r1);
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty(tb));
+            {
+              const int64_t row0 = tile_row0 + col_begin;
+              const int64_t rv = p.N - row0;
+              epi_chunk<MODE, WALK>(p, r0, q, tau, row0, rv >= 32 ? 32 : (rv < 0 ? 0 : (int)rv), gm0, seg, cnt);
+            }
+            {
+              const int64_t row0 = tile_row0 + col_begin + 32;
+              const int64_t rv = p.N - row0;
+              epi_chunk<MODE, WALK>(p, r1, q, tau, row0, rv >= 32 ? 32 : (rv < 0 ? 0 : (int)rv), gm1, seg, cnt);
+            }
+            if (++tb == NB) { tb = 0; tph ^= 1; }
+            continue;
+          }
           tmem_ld_32x32(taddr, r0);
 #pragma unroll 1
           for (int c = 0; c < NCH; c += 2) {

@@ -216,6 +216,22 @@ class ShardedFlatIndex:
         D, I, st, _ = self._search_eager(q, k, normalize, tau, **local_kw)
         return D, I, st
 
+    def release_graphs(self) -> None:
+        """Drop the captured search graphs.  They hold NCCL kernels of the process group's communicator, so they
+        MUST be released before `dist.destroy_process_group()` (the communicator's teardown otherwise waits for
+        them forever: a 2-GPU bench at batch 64 hung at exit that way)."""
+        if self._graphs:
+            self._graphs = {}
+            import gc
+            gc.collect()
+            self._torch.cuda.synchronize(self.local.device)
+
+    def __del__(self):
+        try:
+            self._graphs = {}
+        except Exception:
+            pass
+
     # ---- small batches: capture local search + pack + all-gather + merge once, replay afterwards
     def _graph_entry(self, nq, k, normalize, kw):
         key = (nq, k, normalize, kw)

@@ -23,7 +23,7 @@ def _bf16(a):
     return torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).to(torch.float32).numpy()
 
 
-def _parity(fr, N, Q, k, d=256, seed=0, force_path=0, unit=False, epi_warps=0, walk=None):
+def _parity(fr, N, Q, k, d=256, seed=0, force_path=0, unit=False, epi_warps=0, walk=None, pair_scan=None):
     from oracle.compare import compare_topk
     from oracle.flat import OracleFAISSIndex
     rng = np.random.default_rng(seed)
@@ -36,6 +36,8 @@ def _parity(fr, N, Q, k, d=256, seed=0, force_path=0, unit=False, epi_warps=0, w
         g.index.set_param("epi_warps", epi_warps)
     if walk is not None:
         g.index.set_param("walk", walk)
+    if pair_scan is not None:
+        g.index.set_param("pair_scan", pair_scan)
     g.add(x)
     o = OracleFAISSIndex(d, 'Flat')
     o.add(x)
@@ -168,6 +170,33 @@ def test_two_query_block_filter_scan_both_epilogue_layouts(fr, N, Q, k, d, epi_w
     """Batches above 128 queries run the MQ = 2 filter scan; its 8-warp (one candidate segment per corpus
     split) and 16-warp (one per 64-column half) epilogues must both give the oracle's answer."""
     _parity(fr, N, Q, k, d=d, seed=N + Q, epi_warps=epi_warps)
+
+
+@pytest.mark.parametrize("pair_scan", [0, 1])
+@pytest.mark.parametrize("N,Q,k,d", [(400000, 300, 500, 256), (250000, 1000, 100, 128), (999999, 257, 500, 64),
+                                     (300001, 129, 500, 192), (65000, 600, 500, 256)])
+def test_cta_pair_filter_scan_matches_oracle(fr, N, Q, k, d, pair_scan):
+    """`pair_scan = 1` runs the filter scan of batches above 128 queries on CTA pairs (tcgen05 cta_group::2: 256
+    queries x 256 corpus rows per UMMA, scan_pair.cu); 0 (default) is the one-CTA kernel.  Both give the oracle's answer
+    (odd corpus sizes: the last pair tile is half or partly empty; Q = 129 / 257: an all-padding second block)."""
+    _parity(fr, N, Q, k, d=d, seed=N + Q, pair_scan=pair_scan)
+
+
+def test_cta_pair_scan_and_one_cta_scan_return_identical_results(fr):
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn((700_003, 256), generator=g, device="cuda")
+    q = torch.randn((1500, 256), generator=g, device="cuda")
+    idx = fr.IndexFlatIP(256)
+    idx.add(x, normalize=True)
+    out = []
+    for pair in (1, 0):
+        idx.set_param("pair_scan", pair)
+        assert int(idx.get_param("pair_scan")) == pair
+        D, I, st, _ = idx.search_device(q, 500, normalize=True)
+        assert int((st != 0).sum()) == 0
+        out.append((D.clone(), I.clone()))
+    assert torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][0], out[1][0])
 
 
 @pytest.mark.parametrize("walk", [0, 1])
