@@ -252,6 +252,46 @@ double b2r_tower_get_param(const b2r_tower* t, const char* name);
 int b2r_tower_forward(b2r_tower* t, const int64_t* cat, const float* num, int64_t B, float* out,
                       int32_t* err_flag, void* workspace, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------ Stage-2 ranker -- */
+/* TransformerRanker.forward (transformer_ranker.py:332-380) in eval mode, as called with
+ * stage1_k = 500 candidate rows per user at inference.py:250-255 and faiss_retrieval.py:351-355.
+ * With the sequence length of 1 the reference uses (x.unsqueeze(1), transformer_ranker.py:358) the softmax over
+ * a single key is 1, so self-attention is W_o (W_v x + b_v) + b_o: the host folds it into ONE d_model x d_model
+ * linear map per layer (w_attn, b_attn) and W_q / W_k drop out.  positional_encoding[:, 0] is folded into b_proj.
+ * All weight pointers are HOST fp32, row-major [out, in]. */
+typedef struct b2r_ranker b2r_ranker;
+typedef struct b2r_ranker_weights {
+  int n_user, n_ad;          /* categorical fields of the user / of the ad (6 / 20) */
+  int emb_dim;               /* 32 */
+  int num_numerical;         /* 13 */
+  int d_model, d_ff;         /* 256, 1024 */
+  int n_layers, n_cross;     /* 3 encoder layers, 3 cross layers */
+  int n_tasks, head1, head2; /* 3 heads (ctr, engagement, revenue): d_model -> 256 -> 64 -> 1 */
+  const int64_t* cards;      /* [n_user + n_ad] host: user tables first, in ModuleDict order */
+  const float* const* tables;/* [n_user + n_ad] DEVICE pointers to fp32 [card, emb_dim] tables */
+  const float* w_proj; const float* b_proj;   /* [d_model, (n_user+n_ad)*emb_dim + num_numerical], [d_model] */
+  const float* w_attn; const float* b_attn;   /* [L, d_model, d_model], [L, d_model] (folded, see above) */
+  const float* ln1_g; const float* ln1_b;     /* [L, d_model] */
+  const float* w_fc1; const float* b_fc1;     /* [L, d_ff, d_model], [L, d_ff] */
+  const float* w_fc2; const float* b_fc2;     /* [L, d_model, d_ff], [L, d_model] */
+  const float* ln2_g; const float* ln2_b;     /* [L, d_model] */
+  const float* w_cross; const float* b_cross; /* [C, d_model(out), d_model(in)] = cross_weights[i] TRANSPOSED, [C, d_model] */
+  const float* w_h1; const float* b_h1;       /* [T, head1, d_model], [T, head1] */
+  const float* w_h2; const float* b_h2;       /* [T, head2, head1], [T, head2] */
+  const float* w_h3; const float* b_h3;       /* [T, head2], [T] */
+} b2r_ranker_weights;
+
+int b2r_ranker_create(b2r_ranker** out, const b2r_ranker_weights* w, int device);
+int b2r_ranker_destroy(b2r_ranker* r);
+size_t b2r_ranker_workspace(const b2r_ranker* r, int64_t B);
+/* operand_dtype = 0 fp16 (default) | 1 bf16: as for the towers (B2R_TOWER_SATURATED -> rerun with 1) */
+int b2r_ranker_set_param(b2r_ranker* r, const char* name, double value);
+double b2r_ranker_get_param(const b2r_ranker* r, const char* name);
+/* user_cat int64 [B, n_user]; ad_cat int64 [B, n_ad]; num fp32 [B, num_numerical]; out fp32 [n_tasks, B] = the
+ * heads' raw outputs (the callers apply torch.sigmoid, inference.py:258-260); err_flag as in b2r_tower_forward. */
+int b2r_ranker_forward(b2r_ranker* r, const int64_t* user_cat, const int64_t* ad_cat, const float* num, int64_t B,
+                       float* out, int32_t* err_flag, void* workspace, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------- debug -- */
 /* Test-only helpers (never on the product path). */
 

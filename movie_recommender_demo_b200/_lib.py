@@ -42,6 +42,26 @@ class TowerWeights(C.Structure):
     ]
 
 
+class RankerWeights(C.Structure):
+    """struct b2r_ranker_weights (include/b2retr.h)."""
+    _fields_ = [
+        ("n_user", C.c_int), ("n_ad", C.c_int), ("emb_dim", C.c_int), ("num_numerical", C.c_int),
+        ("d_model", C.c_int), ("d_ff", C.c_int), ("n_layers", C.c_int), ("n_cross", C.c_int),
+        ("n_tasks", C.c_int), ("head1", C.c_int), ("head2", C.c_int),
+        ("cards", C.c_void_p), ("tables", C.c_void_p),
+        ("w_proj", C.c_void_p), ("b_proj", C.c_void_p),
+        ("w_attn", C.c_void_p), ("b_attn", C.c_void_p),
+        ("ln1_g", C.c_void_p), ("ln1_b", C.c_void_p),
+        ("w_fc1", C.c_void_p), ("b_fc1", C.c_void_p),
+        ("w_fc2", C.c_void_p), ("b_fc2", C.c_void_p),
+        ("ln2_g", C.c_void_p), ("ln2_b", C.c_void_p),
+        ("w_cross", C.c_void_p), ("b_cross", C.c_void_p),
+        ("w_h1", C.c_void_p), ("b_h1", C.c_void_p),
+        ("w_h2", C.c_void_p), ("b_h2", C.c_void_p),
+        ("w_h3", C.c_void_p), ("b_h3", C.c_void_p),
+    ]
+
+
 def declared_symbols() -> list[str]:
     """Every function name include/b2retr.h declares."""
     text = HEADER_PATH.read_text()
@@ -98,6 +118,12 @@ def load():
         "b2r_tower_set_param": (i32, [vp, C.c_char_p, dbl]),
         "b2r_tower_get_param": (dbl, [vp, C.c_char_p]),
         "b2r_tower_forward": (i32, [vp, vp, vp, i64, vp, vp, vp, sz, vp]),
+        "b2r_ranker_create": (i32, [C.POINTER(vp), C.POINTER(RankerWeights), i32]),
+        "b2r_ranker_destroy": (i32, [vp]),
+        "b2r_ranker_workspace": (sz, [vp, i64]),
+        "b2r_ranker_set_param": (i32, [vp, C.c_char_p, dbl]),
+        "b2r_ranker_get_param": (dbl, [vp, C.c_char_p]),
+        "b2r_ranker_forward": (i32, [vp, vp, vp, vp, i64, vp, vp, vp, sz, vp]),
         "b2r_debug_scores_tc": (i32, [vp, i32, vp, i32, vp, vp, sz, vp]),
         "b2r_debug_scores_simt": (i32, [vp, i32, vp, i32, vp, vp]),
         "b2r_debug_launch_count": (i64, []),

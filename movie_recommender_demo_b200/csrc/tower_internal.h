@@ -31,6 +31,11 @@ struct b2r_tower {
 namespace b2r {
 // box = {64 columns, box_rows rows}, 128-byte swizzle, 16-bit elements (fp16 or bf16: same layout)
 int make_tmap_f16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int box_rows);
+// out = epilogue(act16 [M, K] · Wᵀ + bias) on the tcgen05 GEMM of tower_mlp.cu.  act16: 16-bit row-major, K a
+// multiple of 64; tmW: tensor map of the 16-bit weights [N, K] with box rows 256 when N % 256 == 0 else 128;
+// mode 0: ReLU -> 16-bit [M, ldo]; 1: row L2-normalise -> fp32 (N <= 256); 2: fp32 [M, ldo] (first n_store columns)
+int launch_linear(const void* act16, const CUtensorMap& tmW, int64_t M, int N, int K, const float* bias, void* out,
+                  int64_t ldo, int n_store, int mode, int32_t* err_flag, int num_sms, cudaStream_t stream, bool bf16);
 // fp32 [rows, cols] row-major, box = {32 columns (128 B), 32 rows}, 128-byte swizzle (TMA stores of the output)
 int make_tmap_f32_out(CUtensorMap* out, const void* base, int64_t rows, int64_t cols);
 // status word bits written by the tower kernels

@@ -151,7 +151,7 @@ struct GemmParams {
   void* out;      // mode 0: fp16 [M, ldo]; mode 1: fp32 [M, ldo]
   int64_t ldo;
   int n_store;    // columns actually stored (mode 1: out_dim <= N)
-  int mode;       // 0: bias + ReLU -> 16-bit   1: bias -> L2 normalise -> fp32
+  int mode;       // 0: bias + ReLU -> 16-bit   1: bias -> L2 normalise -> fp32   2: bias -> fp32 (plain linear)
   int32_t* err_flag;  // kTowerErrSaturate when an fp16 activation clipped
 };
 
@@ -300,18 +300,21 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
         }
       } else {
-        float ss = 0.f;
+        float inv = 1.0f;        // mode 2: plain linear layer, fp32 out
+        if (p.mode == 1) {
+          float ss = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait_dep(r);
+          for (int c = 0; c < BN / 32; ++c) {
+            tmem_ld_32x32(taddr + c * 32, r);
+            tmem_ld_wait_dep(r);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float v = __uint_as_float(r[i]) + bias_s[c * 32 + i];
-            ss = fmaf(v, v, ss);
+            for (int i = 0; i < 32; ++i) {
+              const float v = __uint_as_float(r[i]) + bias_s[c * 32 + i];
+              ss = fmaf(v, v, ss);
+            }
           }
+          inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(||x||, eps)
         }
-        const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(||x||, eps)
         float* obase = reinterpret_cast<float*>(p.out) + n0;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
@@ -435,6 +438,27 @@ int pad_to(int v, int m) { return (v + m - 1) / m * m; }
 
 int make_tmap_f16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int box_rows) {
   return make_tmap_16_impl(out, base, rows, cols, box_rows);
+}
+
+int launch_linear(const void* act16, const CUtensorMap& tmW, int64_t M, int N, int K, const float* bias, void* out,
+                  int64_t ldo, int n_store, int mode, int32_t* err_flag, int num_sms, cudaStream_t stream, bool bf16) {
+  if (N % 128 != 0 || K % 64 != 0) return fail(B2R_EINVAL, "linear: N must be padded to 128 and K to 64");
+  CUtensorMap tmA;
+  int rc = make_tmap_f16_2d(&tmA, act16, M, K, 128);
+  if (rc) return rc;
+  GemmParams gp;
+  gp.M = M;
+  gp.N = N;
+  gp.K = K;
+  gp.bias = bias;
+  gp.out = out;
+  gp.ldo = ldo;
+  gp.n_store = n_store;
+  gp.mode = mode;
+  gp.err_flag = err_flag;
+  if (mode == 1 && N > 256) return fail(B2R_EUNSUPPORTED, "linear: the normalising epilogue needs N <= 256");
+  if (N % 256 == 0 && (mode != 1 || N == 256)) return launch_gemm<256>(tmA, tmW, gp, num_sms, stream, bf16);
+  return launch_gemm<128>(tmA, tmW, gp, num_sms, stream, bf16);
 }
 
 }  // namespace b2r

@@ -3,13 +3,13 @@
 Stage 1 (`recommend_ads`, inference.py:223-235) runs on the B200 kernels: user tower on the
 device -> the embedding stays in HBM (no `.cpu().numpy()` round trip, inference.py:229) ->
 `FAISSIndex.search(k=stage1_k)`.  Stage 2 (the transformer ranker over *random* ad features,
-inference.py:241-263) is outside the hot-path scope and stays whatever stock PyTorch module the
-caller provides; without one, the stage-1 order is returned.
+inference.py:241-263) runs on `transformer_ranker.TransformerRanker` of this package
+(tcgen05 GEMMs, csrc/ranker.cu) — `batch_recommend` ranks the candidates of ALL users in one call — or on
+whatever module with the same forward contract the caller injects; without one, the stage-1 order is returned.
 
 The constructor keeps the reference signature `(model_dir, device)` and its on-disk layout
 (`preprocessor.pkl`, `two_tower_best.pt|two_tower_final.pt`, `faiss_index.bin` (+`.metadata`)).
-The reference's own `data_preprocessing.CriteoDataPreprocessor` and
-`transformer_ranker.TransformerRanker` (CPU ETL and Stage 2 — out of scope, unchanged) are
+The reference's own `data_preprocessing.CriteoDataPreprocessor` (CPU ETL — out of scope, unchanged) is
 imported by name if present on sys.path; every component can also be injected, which is how the
 tests exercise this class without the reference checkout.
 """
@@ -94,11 +94,7 @@ class AdRecommenderInference:
             path = self.model_dir / 'transformer_ranker_final.pt'
         if not path.exists():
             return None
-        try:
-            from transformer_ranker import TransformerRanker  # the reference's Stage-2 module, unchanged
-        except ImportError:
-            self._say("  transformer_ranker.py not importable: stage 2 disabled")
-            return None
+        from .transformer_ranker import TransformerRanker   # same ctor / state-dict keys as the reference's module
         model = TransformerRanker(user_feature_dims=self.user_feature_dims, ad_feature_dims=self.ad_feature_dims,
                                   numerical_dim=self.numerical_dim, embedding_dim=32, d_model=256, num_heads=8,
                                   num_layers=3, d_ff=1024, dropout=0.1)
@@ -158,25 +154,34 @@ class AdRecommenderInference:
                 user_categorical.to(self.device), user_numerical.to(self.device, dtype=torch.float32))
         return self.faiss_index.search(user_emb, k=stage1_k)   # CUDA tensor in, numpy (ids, scores) out
 
-    def _stage2(self, user_categorical, user_numerical, candidate_ids, top_k, return_scores):
-        stage1_k = len(candidate_ids)
+    def _stage2_batch(self, user_categorical, user_numerical, candidate_ids, top_k, return_scores):
+        """Stage 2 for U users at once: candidate_ids [U, stage1_k].  ONE ranker call over U * stage1_k rows
+        (the reference makes one call per user, inference.py:250-255, :309-316).  Returns per user
+        (order [<= top_k], scores dict | None)."""
+        U, stage1_k = candidate_ids.shape[0], candidate_ids.shape[1]
         if self.transformer_ranker is None:
-            order = np.arange(min(top_k, stage1_k))
-            return order, None
-        batch_user_cat = user_categorical.repeat(stage1_k, 1).to(self.device)
-        batch_user_num = user_numerical.repeat(stage1_k, 1).to(self.device)
-        # the reference scores RANDOM ad features here (inference.py:246-248); kept as is
-        batch_ad_cat = torch.randint(0, 200, (stage1_k, 20)).long().to(self.device)
+            return [(np.arange(min(top_k, stage1_k)), None) for _ in range(U)]
+        batch_user_cat = user_categorical.to(self.device).repeat_interleave(stage1_k, dim=0)
+        batch_user_num = user_numerical.to(self.device).repeat_interleave(stage1_k, dim=0)
+        # the reference scores RANDOM ad features here (inference.py:246-248): one draw per user, in user order,
+        # from the global CPU generator - kept as is, so a seeded run consumes the same random stream
+        batch_ad_cat = torch.cat([torch.randint(0, 200, (stage1_k, 20)).long() for _ in range(U)]).to(self.device)
         with torch.no_grad():
             pred = self.transformer_ranker(batch_user_cat, batch_ad_cat, batch_user_num)
-        ctr = torch.sigmoid(pred['ctr']).cpu().numpy()
-        order = np.argsort(ctr)[::-1][:top_k]
-        scores = None
-        if return_scores:
-            scores = {'ctr': ctr[order].tolist(),
-                      'engagement': torch.sigmoid(pred['engagement']).cpu().numpy()[order].tolist(),
-                      'revenue': torch.sigmoid(pred['revenue']).cpu().numpy()[order].tolist()}
-        return order, scores
+        sig = {t: torch.sigmoid(pred[t]).reshape(U, stage1_k).cpu().numpy() for t in ('ctr', 'engagement', 'revenue')}
+        out = []
+        for u in range(U):
+            ctr = sig['ctr'][u]
+            order = np.argsort(ctr)[::-1][:top_k]
+            scores = None
+            if return_scores:
+                scores = {t: sig[t][u][order].tolist() for t in ('ctr', 'engagement', 'revenue')}
+            out.append((order, scores))
+        return out
+
+    def _stage2(self, user_categorical, user_numerical, candidate_ids, top_k, return_scores):
+        return self._stage2_batch(user_categorical, user_numerical, np.asarray(candidate_ids)[None, :], top_k,
+                                  return_scores)[0]
 
     def recommend_ads(self, user_data: dict, top_k: int = 10, stage1_k: int = 500,
                       return_scores: bool = True) -> dict:
@@ -206,11 +211,11 @@ class AdRecommenderInference:
         cat, num = self.preprocess_user_batch(user_data_list)
         ids, dist = self._stage1(cat, num, stage1_k)
         stage1_ms = (time.time() - t0) * 1000 / max(len(user_data_list), 1)
+        t1 = time.time()
+        ranked = self._stage2_batch(cat, num, ids, top_k, True) if len(user_data_list) else []
+        stage2_ms = (time.time() - t1) * 1000 / max(len(user_data_list), 1)
         results = []
-        for i in range(len(user_data_list)):
-            t1 = time.time()
-            order, scores = self._stage2(cat[i:i + 1], num[i:i + 1], ids[i], top_k, True)
-            stage2_ms = (time.time() - t1) * 1000
+        for i, (order, scores) in enumerate(ranked):
             rec = {'ad_ids': ids[i][order].tolist(),
                    'timing': {'stage1_ms': stage1_ms, 'stage2_ms': stage2_ms, 'total_ms': stage1_ms + stage2_ms},
                    'candidate_ids': ids[i], 'stage1_scores': dist[i]}
