@@ -381,8 +381,12 @@ def run_extras(args, torch, dev, peaks, flat_index, q_dev, emit_err):
             for Q in (1, 64, 4096):
                 qq = qs[:Q].contiguous()
                 ms = _timed(torch, lambda: idx.index.search_device(qq, K_TOP, normalize=True), 3, 10)
+                _, _, st, _ = idx.index.search_device(qq, K_TOP, normalize=True)
                 ach = Q * per_q_bytes / ms / 1e6
                 out["batches"][str(Q)] = {"value": Q / ms * 1e3, "ms_per_step": ms,
+                                          # fused list scan (IVF-Flat, Q >= 512): queries its sampled threshold left
+                                          # flagged; FAISSIndex.search re-runs those through the dump path
+                                          "flagged_before_fallback": int((st != 0).sum()),
                                           "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
                                                        "frac": ach / hbm,
                                                        "note": "algorithmic bytes = Q x nprobe x (N/nlist) x bytes/row; "
@@ -423,6 +427,31 @@ def run_extras(args, torch, dev, peaks, flat_index, q_dev, emit_err):
                              "frac": tf / peaks["bf16_tflops"],
                              "hbm": {"algorithmic_bytes": nbytes, "achieved": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / hbm}}}
     guarded("tower_65536", tower)
+
+    # ---- the Stage-2 ranker on the 500 candidates of one user / of 64 users
+    def ranker():
+        sys.path.insert(0, str(ROOT / "tests" / "golden"))
+        from weights import RANKER_CONFIGS, feature_dims, make_ranker_inputs, make_ranker_state
+        from movie_recommender_demo_b200.transformer_ranker import TransformerRanker
+        cfg = RANKER_CONFIGS["cfg1"]
+        user, ad = feature_dims(cfg)
+        m = TransformerRanker(user, ad, cfg["numerical_dim"], embedding_dim=cfg["embedding_dim"], d_model=cfg["d_model"],
+                              num_heads=cfg["num_heads"], num_layers=cfg["num_layers"], d_ff=cfg["d_ff"])
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in make_ranker_state(cfg, 1).items()})
+        m = m.to(dev).eval()
+        per_row = 2.0 * (845 * 256 + 3 * (256 * 256 + 2 * 256 * 1024) + 3 * 256 * 256 + 3 * (256 * 256 + 256 * 64 + 64))
+        out = {"workload": "TransformerRanker (d_model 256, 3 layers, d_ff 1024, 3 cross layers, 3 heads) on stage-1 candidates",
+               "unit": "rows/s", "batches": {}}
+        for B in (K_TOP, 64 * K_TOP):
+            ucat, acat, num = (torch.from_numpy(a).to(dev) for a in make_ranker_inputs(cfg, 2, B))
+            with torch.no_grad():
+                ms = _timed(torch, lambda: m(ucat, acat, num), 5, 20)
+            out["batches"][str(B)] = {"value": B / ms * 1e3, "ms_per_step": ms, "TFLOPs": per_row * B / ms / 1e9}
+        out["value"] = out["batches"][str(64 * K_TOP)]["value"]
+        out["ms_per_step"] = out["batches"][str(64 * K_TOP)]["ms_per_step"]
+        out["operand_dtype"] = m.native_operand_dtype
+        return out
+    guarded("stage2_ranker", ranker)
     return extra
 
 

@@ -572,6 +572,7 @@ int b2r_index_set_param(b2r_index* h, const char* name, double value) {
   else if (n == "force_path") h->force_path = (int)value;
   else if (n == "dense_budget") h->dense_budget = (int64_t)value;
   else if (n == "ivf_sample") h->ivf_sample = (int)value;
+  else if (n == "ivf_fused") h->ivf_fused = value != 0;
   else if (n == "ivf_debug") h->ivf_debug = (int)value;
   else if (n == "pq_scan_path") h->pq_scan_path = (int)value;
   else if (n == "profile") {
@@ -605,6 +606,7 @@ double b2r_index_get_param(const b2r_index* h, const char* name) {
   if (n == "force_path") return h->force_path;
   if (n == "dense_budget") return (double)h->dense_budget;
   if (n == "ivf_sample") return h->ivf_sample;
+  if (n == "ivf_fused") return h->ivf_fused;
   if (n == "num_sms") return h->num_sms;
   if (n == "scan_ms_avg" || n == "scan_launches") {
     // mean device time of the timed filter-scan launches (synchronises on their events)

@@ -200,7 +200,7 @@ __global__ void pair_runs_kernel(const int64_t* __restrict__ coarse, int Q, int 
 __global__ void scatter_pairs_kernel(const int64_t* __restrict__ coarse, int npairs, int nprobe,
                                      unsigned long long* __restrict__ cursor, int* __restrict__ pair_sorted,
                                      const __nv_bfloat16* __restrict__ q16, int d,
-                                     __nv_bfloat16* __restrict__ gq16) {
+                                     __nv_bfloat16* __restrict__ gq16, int* __restrict__ pair_pos) {
   const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (p >= npairs) return;
   const int lane = threadIdx.x & 31;
@@ -209,7 +209,10 @@ __global__ void scatter_pairs_kernel(const int64_t* __restrict__ coarse, int npa
   unsigned long long pos = 0;
   if (lane == 0) pos = atomicAdd(cursor + l, 1ull);
   pos = __shfl_sync(0xffffffffu, pos, 0);
-  if (lane == 0) pair_sorted[pos] = p;
+  if (lane == 0) {
+    pair_sorted[pos] = p;
+    pair_pos[p] = (int)pos;      // inverse map: where the fused path's candidate gather finds this pair's unit lane
+  }
   const uint2* s = reinterpret_cast<const uint2*>(q16 + (size_t)(p / nprobe) * d);
   uint2* o = reinterpret_cast<uint2*>(gq16 + (size_t)pos * d);
   for (int j = lane; j < (d >> 2); j += 32) o[j] = s[j];
@@ -226,7 +229,7 @@ struct IvfUnit {
 
 __global__ void build_units_kernel(const int64_t* __restrict__ list_off, const int64_t* __restrict__ pair_off,
                                    int nlist, IvfUnit* __restrict__ units, int* __restrict__ num_units,
-                                   int max_units, int kUnitTiles) {
+                                   int max_units, int kUnitTiles, int* __restrict__ list_unit0) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= nlist) return;
   const int64_t q0 = pair_off[l], q1 = pair_off[l + 1];
@@ -236,6 +239,7 @@ __global__ void build_units_kernel(const int64_t* __restrict__ list_off, const i
   const int tchunks = (tiles + kUnitTiles - 1) / kUnitTiles;
   const int qblocks = (int)((q1 - q0 + kQBlock - 1) / kQBlock);
   const int base = atomicAdd(num_units, tchunks * qblocks);
+  list_unit0[l] = base;          // unit of (query block qb, tile chunk tc) of this list = base + qb * tchunks + tc
   int u = base;
   for (int qb = 0; qb < qblocks; ++qb) {
     for (int tc = 0; tc < tchunks; ++tc, ++u) {
@@ -276,8 +280,31 @@ struct IvfScanParams {
   const int64_t* pair_out;    // pair id -> offset of its score run in scorebuf
   float* scorebuf;
   int debug;                  // profiling experiments only (set_param ivf_debug): 1 = skip the score stores
+  // sample = 1: only the FIRST tile of each list (units that start at the list's first row) is scored, dumped
+  // into the head of every pair's run: the fused path's threshold estimate
+  int sample;
+  // FILTER instantiation (fused path): scores >= tau[query] are appended to a private candidate segment per
+  // (unit, lane = pair, 64-column half) inside the pair's run of `pool`; nothing else reaches HBM
+  const float* tau;           // [Q] per-query candidate threshold
+  int nprobe;
+  uint2* pool;                // [Q * smax] (score bits, stored row), same run geometry as scorebuf
+  int* seg_count;             // [max_units][2][128] entries per segment
 };
 
+// tiles of a unit the scan processes (0: the unit is skipped by every warp role alike)
+__device__ __forceinline__ int ivf_unit_tiles(const IvfUnit& un, int sample) {
+  if (!sample) return un.ntiles;
+  return un.xrow0 == un.xlist0 ? 1 : 0;
+}
+// rows of a unit that fall into the first 64-column half of its tiles (the second half's segment starts there)
+__device__ __forceinline__ int ivf_half0_rows(const IvfUnit& un) {
+  int rows = un.xend - un.xrow0;
+  if (rows > un.ntiles * kTileRows) rows = un.ntiles * kTileRows;
+  const int full = rows / kTileRows, rem = rows % kTileRows;
+  return full * 64 + (rem < 64 ? rem : 64);
+}
+
+template <bool FILTER>
 __global__ void __launch_bounds__(kIvfThreads, 1)
 ivf_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX,
                 const IvfScanParams p) {
@@ -319,11 +346,13 @@ ivf_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       bool first = true;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
         const IvfUnit un = p.units[u];
+        const int ntiles = ivf_unit_tiles(un, p.sample);
+        if (ntiles == 0) continue;
         if (!first) { mbar_wait(bar_qempty, qe_par, 21); qe_par ^= 1; }
         first = false;
         mbar_arrive_expect_tx(bar_qfull, (uint32_t)(KC * 16384));
         for (int kc = 0; kc < KC; ++kc) tma_load_2d(sA + kc * 16384, &tmQ, kc * kKChunk, un.qrow0, bar_qfull);
-        for (int t = 0; t < un.ntiles; ++t) {
+        for (int t = 0; t < ntiles; ++t) {
           for (int kc = 0; kc < KC; ++kc) {
             mbar_wait(bar_empty(slot), ph ^ 1, 22);
             mbar_arrive_expect_tx(bar_full(slot), 16384u);
@@ -342,7 +371,8 @@ ivf_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       int slot = 0, tb = 0;
       uint32_t ph = 0, tph = 0, qf_par = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int ntiles = p.units[u].ntiles;
+        const int ntiles = ivf_unit_tiles(p.units[u], p.sample);
+        if (ntiles == 0) continue;
         mbar_wait(bar_qfull, qf_par, 23);
         qf_par ^= 1;
         tc_fence_after_sync();
@@ -368,7 +398,11 @@ ivf_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           __syncwarp();
           if (++tb == NB) { tb = 0; tph ^= 1; }
         }
-        if (u + (int)gridDim.x < units) {
+        // the producer waits for this before it overwrites the query block: only if this CTA has a later unit
+        bool more = false;
+        for (int v = u + (int)gridDim.x; v < units && !more; v += (int)gridDim.x)
+          more = ivf_unit_tiles(p.units[v], p.sample) > 0;
+        if (more) {
           if (elect_one()) umma_commit(bar_qempty);
           __syncwarp();
         }
@@ -388,14 +422,67 @@ ivf_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t tph = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const IvfUnit un = p.units[u];
+      const int ntiles_u = ivf_unit_tiles(un, p.sample);
+      if (ntiles_u == 0) continue;
       const int ql = quarter * 32 + lane;
       const bool warp_active = quarter * 32 < un.nq;
       // offset (in floats, < 2^32: the score buffer is capped at 6 GB) of this lane's query run
       uint32_t my_run = kNoRun;
-      if (ql < un.nq) my_run = (uint32_t)p.pair_out[p.pair_sorted[un.qrow0 + ql]];
-      for (int t = 0; t < un.ntiles; ++t) {
+      float my_tau = INFINITY;
+      if (ql < un.nq) {
+        const int pair = p.pair_sorted[un.qrow0 + ql];
+        my_run = (uint32_t)p.pair_out[pair];
+        if (FILTER) my_tau = p.tau[pair / p.nprobe];
+      }
+      // FILTER: this lane's private candidate segment for (unit, column half g) inside its pair's run
+      uint2* seg = nullptr;
+      int cnt = 0;
+      if (FILTER && my_run != kNoRun)
+        seg = p.pool + (size_t)my_run + (size_t)(un.xrow0 - un.xlist0) + (size_t)(g ? ivf_half0_rows(un) : 0);
+      for (int t = 0; t < ntiles_u; ++t) {
         mbar_wait(bar_tfull(tb), tph, 26);
         tc_fence_after_sync();
+        if (FILTER) {
+          if (warp_active) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tb * 128 + col_begin);
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32(taddr, r0);
+            tmem_ld_32x32(taddr + 32, r1);
+            tmem_ld_wait_dep(r0);
+            tmem_ld_wait_dep(r1);
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty(tb));
+            const int row0 = un.xrow0 + t * kTileRows + col_begin;
+            auto scan32 = [&](const uint32_t (&r)[32], int base_row) {
+              const int nvalid = un.xend - base_row;     // rows of this chunk that belong to the list
+#pragma unroll
+              for (int s8 = 0; s8 < 32; s8 += 8) {
+                const float a = fmax3(__uint_as_float(r[s8]), __uint_as_float(r[s8 + 1]), __uint_as_float(r[s8 + 2]));
+                const float b = fmax3(__uint_as_float(r[s8 + 3]), __uint_as_float(r[s8 + 4]), __uint_as_float(r[s8 + 5]));
+                const float c = fmaxf(__uint_as_float(r[s8 + 6]), __uint_as_float(r[s8 + 7]));
+                if (fmax3(a, b, c) >= my_tau) {
+#pragma unroll
+                  for (int i = s8; i < s8 + 8; ++i)
+                    if (__uint_as_float(r[i]) >= my_tau && i < nvalid) {
+                      seg[cnt] = make_uint2(r[i], (uint32_t)(base_row + i));
+                      ++cnt;
+                    }
+                }
+              }
+            };
+            if (seg) {     // my_tau = +inf for idle lanes, but NaN scores must not reach a null segment either
+              scan32(r0, row0);
+              scan32(r1, row0 + 32);
+            }
+          } else {
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty(tb));
+          }
+          if (++tb == NB) { tb = 0; tph ^= 1; }
+          continue;
+        }
         if (warp_active) {
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tb * 128 + col_begin);
           uint32_t r[32];
@@ -445,6 +532,7 @@ ivf_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         if (++tb == NB) { tb = 0; tph ^= 1; }
       }
+      if (FILTER && seg) p.seg_count[(size_t)u * 256 + g * 128 + ql] = cnt;
     }
   }
   __syncwarp();
@@ -475,19 +563,23 @@ ivf_threshold_kernel(const float* __restrict__ scorebuf, int64_t smax, const int
   int64_t* run_end = runs;
   int64_t* run_x0 = runs + nprobe;
   int64_t* run_len = runs + 2 * nprobe;
+  // one thread per probe for the (dependent) coarse -> list_off loads: serialised in one thread they were
+  // ~20 us of every query's 28-39 us at nprobe = 32
+  for (int j = threadIdx.x; j < nprobe; j += blockDim.x) {
+    const int64_t l = coarse[(size_t)q * nprobe + j];
+    int64_t len = 0, x0 = 0;
+    if (l >= 0) {
+      x0 = list_off[l];
+      len = list_off[l + 1] - x0;
+    }
+    run_x0[j] = x0;
+    run_len[j] = len;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     int64_t cum = 0;
     for (int j = 0; j < nprobe; ++j) {
-      const int64_t l = coarse[(size_t)q * nprobe + j];
-      int64_t len = 0;
-      if (l >= 0) {
-        len = list_off[l + 1] - list_off[l];
-        run_x0[j] = list_off[l];
-      } else {
-        run_x0[j] = 0;
-      }
-      run_len[j] = len;
-      cum += (len + 3) & ~(int64_t)3;
+      cum += (run_len[j] + 3) & ~(int64_t)3;
       run_end[j] = cum;
     }
     s_rem = m;
@@ -624,6 +716,223 @@ ivf_threshold_kernel(const float* __restrict__ scorebuf, int64_t smax, const int
   if (threadIdx.x == 0) tau[q] = t;
   __syncthreads();
   if (threadIdx.x == 0) cand_count[q] = s_count;
+}
+
+// ------------------------------------------------------------ fused path: threshold + gather ---
+// Threshold of the fused list scan, one CTA per query.  The sample pass scored the first `S` rows of every probed
+// list (a list's rows are in insertion order: a random sample of the list).  Lists differ in length AND in how
+// close they are to the query, so every sampled score of list j stands for len_j / s_j rows: tau = the score at
+// which the WEIGHTED count of sampled scores reaches c_target (the candidates the filter scan should pass).
+// When the query scans no more rows than the candidate buffer holds, tau = -inf (everything is a candidate).
+constexpr int kIvfTauThreads = 512;
+constexpr int kIvfTauMaxKeys = 8192;
+constexpr int kIvfTauWShift = 6;     // fixed-point weights (rows per sampled row, 1/64 steps): integer histograms
+__global__ void __launch_bounds__(kIvfTauThreads)
+ivf_sample_tau_kernel(const float* __restrict__ scorebuf, int64_t smax, const int64_t* __restrict__ coarse, int nprobe,
+                      const int64_t* __restrict__ list_off, int S, int c_target, int take_all_below,
+                      float* __restrict__ tau) {
+  extern __shared__ __align__(16) uint8_t tsm[];
+  uint32_t* keys = reinterpret_cast<uint32_t*>(tsm);                              // [ns] order-preserving score keys
+  uint32_t* wk = keys + kIvfTauMaxKeys;                                           // [ns] weight of each key
+  uint32_t* wgt = wk + kIvfTauMaxKeys;                                            // [nprobe] weight of a sample of list j
+  int* sstart = reinterpret_cast<int*>(wgt + nprobe);                             // [nprobe + 1] prefix of sample sizes
+  int* rstart = sstart + nprobe + 1;                                              // [nprobe] run start (floats)
+  __shared__ unsigned long long hist[256];
+  __shared__ unsigned long long s_rem;
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_total_rows, s_done;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  // list lengths: one thread per probe (the loads are two dependent round trips each - never serialise them)
+  for (int j = tid; j < nprobe; j += blockDim.x) {
+    const int64_t l = coarse[(size_t)q * nprobe + j];
+    rstart[j] = l >= 0 ? (int)(list_off[l + 1] - list_off[l]) : 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int64_t cum = 0, rows = 0;
+    int ns = 0;
+    for (int j = 0; j < nprobe; ++j) {
+      const int64_t len = rstart[j];
+      const int sj = (int)(len < S ? len : S);
+      sstart[j] = ns;
+      rstart[j] = (int)cum;
+      wgt[j] = sj > 0 ? (uint32_t)((len << kIvfTauWShift) / sj) : 0u;
+      ns += sj;
+      rows += len;
+      cum += (len + 3) & ~(int64_t)3;
+    }
+    sstart[nprobe] = ns;
+    s_total_rows = (int)(rows < 0x7fffffff ? rows : 0x7fffffff);
+  }
+  __syncthreads();
+  const int ns = sstart[nprobe];
+  if (s_total_rows <= take_all_below || ns == 0) {
+    if (tid == 0) tau[q] = -INFINITY;
+    return;
+  }
+  const float* row = scorebuf + (size_t)q * smax;
+  for (int i = tid; i < ns; i += blockDim.x) {
+    int lo = 0, hi = nprobe - 1;          // largest j with sstart[j] <= i
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (sstart[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    keys[i] = f2ord(row[rstart[lo] + (i - sstart[lo])]);
+    wk[i] = wgt[lo];
+  }
+  // at least ~32 sampled scores above the threshold (a rank-3 estimate would scatter the candidate count by
+  // +-60 %), never more candidates than 5/7 of what the buffer takes
+  float target = fmaxf((float)c_target, 32.f * (float)s_total_rows / (float)ns);
+  target = fminf(target, (float)(take_all_below * 5 / 7));
+  if (tid == 0) {
+    s_rem = (unsigned long long)((double)target * (double)(1 << kIvfTauWShift));
+    s_prefix = 0;
+    s_done = 0;
+  }
+  __syncthreads();
+  // MSB-first WEIGHTED radix select: the key at which the cumulative weight (from the top) reaches the target.
+  // Three byte passes: the low byte stays zero = a lower bound 2^-15 relative below that score (a few more
+  // candidates, one pass less).
+  uint32_t prefix = 0, mask = 0;
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0ull;
+    __syncthreads();
+    // a query's scores share their leading key bytes, so most lanes of a warp hit the SAME bin: aggregate per
+    // warp (one shared atomic per distinct bin and warp) instead of serialising thousands of atomics on one word
+    const int ns_pad = (ns + 31) & ~31;
+    for (int i = tid; i < ns_pad; i += blockDim.x) {
+      uint32_t key = 0, w = 0;
+      bool on = false;
+      if (i < ns) {
+        key = keys[i];
+        on = (key & mask) == prefix;
+        w = wk[i];
+      }
+      const int bin = (int)((key >> shift) & 255u);
+      unsigned active = __ballot_sync(0xffffffffu, on);
+      while (active) {
+        const int leader = __ffs(active) - 1;
+        const int lbin = __shfl_sync(0xffffffffu, bin, leader);
+        const bool mine = on && bin == lbin;
+        const unsigned long long sum = (unsigned long long)__reduce_add_sync(0xffffffffu, mine ? (w >> 4) : 0u) << 4;
+        if ((tid & 31) == leader) atomicAdd(&hist[lbin], sum);
+        active &= ~__ballot_sync(0xffffffffu, mine);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long rem = s_rem, cum = 0;
+      int b = 255;
+      for (; b > 0; --b) {
+        if (cum + hist[b] >= rem) break;
+        cum += hist[b];
+      }
+      if (b == 0 && cum + hist[0] < rem) s_done = 1;     // the whole sample weighs less than the target: take everything
+      s_rem = rem - cum;
+      s_prefix = prefix | ((uint32_t)b << shift);
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    mask |= 255u << shift;
+    if (s_done) break;
+  }
+  if (tid == 0) tau[q] = s_done ? -INFINITY : ord2f(prefix);
+}
+
+// Collects a query's candidates from the private segments the filter scan wrote -- one per (unit, pair lane,
+// column half), inside the pair's run of `pool` -- into its single candidate list for select_rescore.
+constexpr int kIvfGatherThreads = 256;
+constexpr int kIvfGatherMaxSub = 4096;
+__global__ void __launch_bounds__(kIvfGatherThreads)
+ivf_gather_kernel(const int64_t* __restrict__ coarse, int nprobe, const int64_t* __restrict__ list_off,
+                  const int64_t* __restrict__ pairoff, const int* __restrict__ pair_pos,
+                  const int* __restrict__ list_unit0, int unit_tiles, const uint2* __restrict__ pool, int64_t smax,
+                  const int* __restrict__ seg_count, uint2* __restrict__ cand, int* __restrict__ cand_count, int cap) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  int* sub0 = reinterpret_cast<int*>(gsm);              // [nprobe + 1] first sub-segment of pair j
+  int* rstart = sub0 + nprobe + 1;                      // [nprobe] run start of pair j (entries, relative to the query)
+  int* cnt = rstart + nprobe;                           // [kIvfGatherMaxSub + 1] -> exclusive prefix
+  uint32_t* src = reinterpret_cast<uint32_t*>(cnt + kIvfGatherMaxSub + 1);   // [kIvfGatherMaxSub] segment start
+  __shared__ int s_nsub, s_total;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  for (int j = tid; j < nprobe; j += blockDim.x) {     // one thread per probe: the loads are dependent round trips
+    const int64_t l = coarse[(size_t)q * nprobe + j];
+    rstart[j] = l >= 0 ? (int)(list_off[l + 1] - list_off[l]) : 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int64_t cum = 0;
+    int ns = 0;
+    for (int j = 0; j < nprobe; ++j) {
+      const int64_t len = rstart[j];
+      sub0[j] = ns;
+      rstart[j] = (int)cum;
+      const int tiles = (int)((len + kTileRows - 1) / kTileRows);
+      ns += 2 * ((tiles + unit_tiles - 1) / unit_tiles);
+      cum += (len + 3) & ~(int64_t)3;
+    }
+    sub0[nprobe] = ns;
+    s_nsub = ns;
+  }
+  __syncthreads();
+  const int nsub = s_nsub;
+  if (nsub > kIvfGatherMaxSub) {       // cannot happen with the planner's limits; reported as an overflow
+    if (tid == 0) cand_count[q] = cap + 1;
+    return;
+  }
+  for (int ss = tid; ss < nsub; ss += blockDim.x) {
+    int lo = 0, hi = nprobe - 1;       // pair j of this sub-segment
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (sub0[mid] <= ss) lo = mid; else hi = mid - 1;
+    }
+    const int j = lo, rel = ss - sub0[j], tc = rel >> 1, h = rel & 1;
+    const int64_t l = coarse[(size_t)q * nprobe + j];
+    const int64_t x0 = list_off[l], x1 = list_off[l + 1];
+    const int tiles = (int)((x1 - x0 + kTileRows - 1) / kTileRows);
+    const int tchunks = (tiles + unit_tiles - 1) / unit_tiles;
+    const int pos = pair_pos[(size_t)q * nprobe + j] - (int)pairoff[l];
+    const int u = list_unit0[l] + (pos / kQBlock) * tchunks + tc;
+    IvfUnit un;
+    un.xrow0 = (int)(x0 + (int64_t)tc * unit_tiles * kTileRows);
+    const int tl = tiles - tc * unit_tiles;
+    un.ntiles = tl < unit_tiles ? tl : unit_tiles;
+    un.xend = (int)x1;
+    un.xlist0 = (int)x0;
+    cnt[ss] = seg_count[(size_t)u * 256 + h * 128 + (pos % kQBlock)];
+    src[ss] = (uint32_t)(rstart[j] + (un.xrow0 - un.xlist0) + (h ? ivf_half0_rows(un) : 0));
+  }
+  __syncthreads();
+  if (tid < 32) {                      // exclusive scan of the counts, 32 at a time
+    int carry = 0;
+    for (int b = 0; b < nsub; b += 32) {
+      const int idx = b + tid;
+      const int c = idx < nsub ? cnt[idx] : 0;
+      int v = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (tid >= o) v += t;
+      }
+      if (idx < nsub) cnt[idx] = carry + v - c;
+      carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+    if (tid == 0) { cnt[nsub] = carry; s_total = carry; }
+  }
+  __syncthreads();
+  const int total = s_total;
+  const int n = total < cap ? total : cap;
+  const uint2* qpool = pool + (size_t)q * smax;
+  for (int i = tid; i < n; i += blockDim.x) {   // one thread per candidate: every load of the gather in flight at once
+    int lo = 0, hi = nsub - 1;                  // largest ss with cnt[ss] <= i
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (cnt[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    cand[(size_t)q * cap + i] = qpool[src[lo] + (uint32_t)(i - cnt[lo])];
+  }
+  if (tid == 0) cand_count[q] = total;
 }
 
 // --------------------------------------------------------------------- host side ---
@@ -943,6 +1252,10 @@ namespace {
 struct IvfPlan {
   int nprobe = 1, chunk = 0, qpad = 0, max_units = 0, cap = 4096, c_target = 0, sample_stride = 1;
   int64_t smax = 0, pairs_pad = 0;
+  // fused path (IVF-Flat): sample pass -> per-query threshold -> filter scan -> candidate gather
+  bool fused = false;
+  int sample_rows = 0;      // rows of every probed list the sample pass scores
+  size_t off_pair_pos = 0, off_list_unit0 = 0, off_seg_count = 0;
   size_t off_cstatus = 0;
   size_t off_q16, off_q32, off_qnorm, off_coarse, off_cdist, off_pair_out, off_row_len, off_listcnt, off_pairoff,
       off_cursor, off_pair_sorted, off_gq16, off_units, off_nunits, off_tau, off_count, off_cand, off_score,
@@ -976,20 +1289,31 @@ IvfPlan make_ivf_plan(const b2r_index* h, int q, int k, int nprobe) {
   pl.sample_stride = 1;
   while (pl.sample_stride < 16 && ct / (pl.sample_stride * 2) >= 64) pl.sample_stride *= 2;
   if (h->ivf_sample == 0) pl.sample_stride = 1;
-  const int64_t budget = (int64_t)6 << 30;   // score runs of one query chunk (fewer chunks = fewer passes over the lists)
-  int64_t qc = budget / (pl.smax * 4);
+  // units <= sum over lists ceil(nq/128) * ceil(tiles/8); bound: (pairs/128 + nlist) query blocks,
+  // each with <= ceil(max_list_tiles / 8) tile chunks
+  const int64_t max_tiles = sz.empty() ? 1 : ceil_div(sz[0] > 0 ? sz[0] : 1, kTileRows);
+  // fused path: the filter scan appends candidates to private segments inside the pair runs (8 bytes per slot
+  // instead of 4 per dumped score, touched only where a candidate lands).  Needs the sample of every probed list
+  // to fit the threshold kernel's sort buffer and the query's segment list to fit the gather kernel's.
+  pl.sample_rows = std::max(4, std::min(128, (kIvfTauMaxKeys / nprobe) & ~3));
+  int64_t worst_sub = 0;
+  for (int i = 0; i < nprobe && i < (int)sz.size(); ++i)
+    worst_sub += 2 * ceil_div(ceil_div(sz[i] > 0 ? sz[i] : 1, kTileRows), kUnitTilesSmallQ);
+  pl.fused = h->kind == B2R_KIND_IVF_FLAT && h->ivf_fused && h->rescore && (int64_t)nprobe * pl.sample_rows <= kIvfTauMaxKeys &&
+             worst_sub <= kIvfGatherMaxSub;
+  const int64_t slot_bytes = pl.fused ? 8 : 4;
+  const int64_t budget = ((int64_t)6 << 30) / 4 * slot_bytes;   // runs of one query chunk (fewer chunks = fewer passes over the lists)
+  int64_t qc = budget / (pl.smax * slot_bytes);
   if (qc < 1) qc = 1;
   if (qc > 8192) qc = 8192;
   pl.chunk = (int)(q < qc ? q : qc);
   pl.qpad = (int)align_up((size_t)pl.chunk, 128);
   const int64_t pairs = (int64_t)pl.chunk * nprobe;
   pl.pairs_pad = pairs + kQBlock;
-  // units <= sum over lists ceil(nq/128) * ceil(tiles/8); bound: (pairs/128 + nlist) query blocks,
-  // each with <= ceil(max_list_tiles / 8) tile chunks
-  const int64_t max_tiles = sz.empty() ? 1 : ceil_div(sz[0] > 0 ? sz[0] : 1, kTileRows);
   int64_t mu = (pairs / kQBlock + std::min<int64_t>(h->nlist, pairs) + 1) * ceil_div(max_tiles, kUnitTilesSmallQ);
   if (mu > (1 << 24)) mu = 1 << 24;
   pl.max_units = (int)mu;
+  if (mu * 1024 > ((int64_t)1 << 30)) pl.fused = false;    // segment counters: 1 KB per unit
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = off; off = align_up(off + b, 256); return o; };
   pl.off_q16 = take((size_t)pl.qpad * h->d * 2);
@@ -1010,7 +1334,10 @@ IvfPlan make_ivf_plan(const b2r_index* h, int q, int k, int nprobe) {
   pl.off_tau = take((size_t)pl.chunk * 4);
   pl.off_count = take((size_t)pl.chunk * 4);
   pl.off_cand = take((size_t)pl.chunk * pl.cap * 8);
-  pl.off_score = take((size_t)pl.chunk * pl.smax * 4);
+  pl.off_score = take((size_t)pl.chunk * pl.smax * (pl.fused ? 8 : 4));   // dumped scores, or the candidate pool (its head doubles as the sample's score buffer)
+  pl.off_pair_pos = take((size_t)pairs * 4);
+  pl.off_list_unit0 = take((size_t)h->nlist * 4);
+  pl.off_seg_count = take(pl.fused ? (size_t)pl.max_units * 1024 : 0);
   {
     // the search-time coarse quantiser always takes the flat index's DENSE path (dump + exact k-th): nlist <= 65536
     // always fits, and the probed list set must never depend on a sampled threshold (see ivf_search)
@@ -1041,7 +1368,10 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
   int dev = 0;
   B2R_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
-    B2R_CUDA(cudaFuncSetAttribute(ivf_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvfSmem));
+    B2R_CUDA(cudaFuncSetAttribute(ivf_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvfSmem));
+    B2R_CUDA(cudaFuncSetAttribute(ivf_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIvfSmem));
+    B2R_CUDA(cudaFuncSetAttribute(ivf_sample_tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    B2R_CUDA(cudaFuncSetAttribute(ivf_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     configured[dev & 63] = true;
   }
   for (int q0 = 0; q0 < q; q0 += pl.chunk) {
@@ -1092,6 +1422,10 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     pair_runs_kernel<<<(unsigned)ceil_div(qc, 128), 128, 0, stream>>>(coarse, qc, np, h->list_off, pl.smax, pair_out,
                                                                       row_len, listcnt);
     B2R_CHECK_LAUNCH("pair_runs_kernel");
+    // Below 512 queries a list is scanned for a handful of pairs: the dump is small, and the fused path's two
+    // extra launches (sample scan, segment gather) cost more than the score round trip saves (measured at
+    // 10M x 256, nlist 4096, nprobe 32: Q=64 0.53 vs 0.52 ms, Q=4096 2.26 vs 2.57 ms).
+    const bool fused = pl.fused && !is_pq && qc >= 512;
     if (is_pq) {
       // ADC scan: one CTA per (query, probed list) pair, LUT in shared memory (ivfpq.cu)
       if ((rc = pq_scan(h, qc, npairs, q32, coarse, np, pair_out, reinterpret_cast<float*>(ws + pl.off_qtab), scorebuf,
@@ -1100,11 +1434,14 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     } else {
     scan_lists_kernel<<<1, 1024, 0, stream>>>(listcnt, nullptr, h->nlist, pairoff, cursor);
     B2R_CHECK_LAUNCH("scan_lists_kernel(pairs)");
+    int* pair_pos = reinterpret_cast<int*>(ws + pl.off_pair_pos);          // inverse maps for the fused path's gather
+    int* list_unit0 = reinterpret_cast<int*>(ws + pl.off_list_unit0);
+    const int unit_tiles = qc >= 512 ? kUnitTilesLargeQ : kUnitTilesSmallQ;
     scatter_pairs_kernel<<<(unsigned)ceil_div(npairs, 8), 256, 0, stream>>>(
-        coarse, npairs, np, reinterpret_cast<unsigned long long*>(cursor), pair_sorted, q16, d, gq16);
+        coarse, npairs, np, reinterpret_cast<unsigned long long*>(cursor), pair_sorted, q16, d, gq16, pair_pos);
     B2R_CHECK_LAUNCH("scatter_pairs_kernel");
     build_units_kernel<<<(unsigned)ceil_div(h->nlist, 128), 128, 0, stream>>>(
-        h->list_off, pairoff, h->nlist, units, nunits, pl.max_units, qc >= 512 ? kUnitTilesLargeQ : kUnitTilesSmallQ);
+        h->list_off, pairoff, h->nlist, units, nunits, pl.max_units, unit_tiles, list_unit0);
     B2R_CHECK_LAUNCH("build_units_kernel");
     CUtensorMap tmQ;
     if ((rc = make_tmap_bf16_rows(&tmQ, gq16, pl.pairs_pad, d))) return rc;
@@ -1118,15 +1455,42 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     sp.pair_out = pair_out;
     sp.scorebuf = scorebuf;
     sp.debug = h->ivf_debug;
-    ivf_scan_kernel<<<h->num_sms, kIvfThreads, kIvfSmem, stream>>>(tmQ, h->tmX, sp);
-    B2R_CHECK_LAUNCH("ivf_scan_kernel");
+    sp.sample = 0;
+    sp.tau = tau;
+    sp.nprobe = np;
+    sp.pool = reinterpret_cast<uint2*>(scorebuf);
+    sp.seg_count = reinterpret_cast<int*>(ws + pl.off_seg_count);
+    if (fused) {
+      // 1. sample: the first tile of every probed list, dumped into the head of each pair's run
+      sp.sample = 1;
+      ivf_scan_kernel<false><<<h->num_sms, kIvfThreads, kIvfSmem, stream>>>(tmQ, h->tmX, sp);
+      B2R_CHECK_LAUNCH("ivf_scan_kernel(sample)");
+      // 2. per-query threshold from the length-weighted sample
+      ivf_sample_tau_kernel<<<qc, kIvfTauThreads, (size_t)kIvfTauMaxKeys * 8 + (size_t)np * 12 + 16, stream>>>(
+          scorebuf, pl.smax, coarse, np, h->list_off, pl.sample_rows, pl.c_target, pl.cap - pl.cap / 8, tau);
+      B2R_CHECK_LAUNCH("ivf_sample_tau_kernel");
+      // 3. the list scan with the threshold in its epilogue: only candidates leave the SM
+      sp.sample = 0;
+      ivf_scan_kernel<true><<<h->num_sms, kIvfThreads, kIvfSmem, stream>>>(tmQ, h->tmX, sp);
+      B2R_CHECK_LAUNCH("ivf_scan_kernel(filter)");
+      // 4. segments -> one candidate list per query
+      ivf_gather_kernel<<<qc, kIvfGatherThreads, (size_t)(2 * np + 1) * 4 + (size_t)(2 * kIvfGatherMaxSub + 1) * 4 + 16, stream>>>(
+          coarse, np, h->list_off, pairoff, pair_pos, list_unit0, unit_tiles, reinterpret_cast<const uint2*>(scorebuf),
+          pl.smax, sp.seg_count, cand, count, pl.cap);
+      B2R_CHECK_LAUNCH("ivf_gather_kernel");
+    } else {
+      ivf_scan_kernel<false><<<h->num_sms, kIvfThreads, kIvfSmem, stream>>>(tmQ, h->tmX, sp);
+      B2R_CHECK_LAUNCH("ivf_scan_kernel");
     }
+    }
+    if (!fused) {
     ivf_threshold_kernel<<<qc, kIvfSelThreads, (size_t)np * 24, stream>>>(
         scorebuf, pl.smax, row_len, k, coarse, np, h->list_off, tau, count, cand, pl.cap,
         (h->rescore && !is_pq) ? qnorm : nullptr, h->maxnorm, (float)(h->scan_fp16 == 1 ? h->eps_fp16 : h->eps),
         is_pq ? 4 : 3,    // IVF-Flat re-scores the window, a 2^-15-relative lower bound suffices; PQ needs the exact k-th
         pl.sample_stride, pl.c_target);
     B2R_CHECK_LAUNCH("ivf_threshold_kernel");
+    }
     SelectParams sel;
     memset(&sel, 0, sizeof(sel));
     sel.Q = qc;

@@ -18,7 +18,34 @@ from .faiss_retrieval import METRIC_INNER_PRODUCT, METRIC_L2, _DeviceIndex
 class IndexIVFFlat(_DeviceIndex):
     kind = _lib.KIND_IVF_FLAT
     metric = METRIC_INNER_PRODUCT
-    _supports_retry = False
+    # The fused list scan (sample pass -> per-query threshold -> filter in the scan's epilogue) can leave a query
+    # flagged (too few candidates / candidate buffer overflow / threshold above the provable rescore window).
+    # Flagged queries are re-run through the dump path, whose exact in-kernel fallback always succeeds.
+    _supports_retry = True
+    _collective_retry = False    # sharded.py: the caller-threshold retry protocol is the flat index's only
+
+    def _retry(self, qt, k, normalize, nprobe, st, tau_retry, D_dev, I_dev, D_np, I_np):
+        from .faiss_retrieval import _RETRY_BITS
+        torch = self._torch
+        bad = np.nonzero(st & _RETRY_BITS)[0]
+        self.last_retries = 0
+        if bad.size == 0 or int(self.get_param("ivf_fused")) == 0:
+            return st
+        bad_t = torch.as_tensor(bad, device=self.device)
+        self.set_param("ivf_fused", 0)
+        try:
+            D2, I2, st2, _ = self._search_prepared(qt.index_select(0, bad_t), k, normalize=normalize, nprobe=nprobe)
+        finally:
+            self.set_param("ivf_fused", 1)
+        if D_dev is not None:
+            D_dev.index_copy_(0, bad_t, D2)
+            I_dev.index_copy_(0, bad_t, I2)
+        else:
+            D_np[bad] = D2.cpu().numpy()
+            I_np[bad] = I2.cpu().numpy()
+        st[bad] = st2.cpu().numpy()
+        self.last_retries = 1
+        return st
 
     def __init__(self, d: int, nlist: int, *, device=None, pq_m: int = 0):
         self.nlist = int(nlist)
@@ -78,6 +105,8 @@ class IndexIVFPQ(IndexIVFFlat):
     """faiss.IndexIVFPQ(IndexFlatIP(d), d, nlist, m, 8) — default metric L2 (faiss_retrieval.py:57-63)."""
     kind = _lib.KIND_IVF_PQ
     metric = METRIC_L2
+
+    _supports_retry = False     # ADC scan: no fused filter, the threshold kernel's exact fallback is in-kernel
 
     def __init__(self, d: int, nlist: int, m: int = 8, *, device=None):
         self.pq_m = int(m)

@@ -283,7 +283,8 @@ class ShardedFlatIndex:
         D, I = D.clone(), I.clone()
         st_h = st.cpu().numpy().copy()           # synchronises
         retries = 0
-        while self.world > 1 and self.local._supports_retry and retries < _MAX_RETRIES:
+        while (self.world > 1 and self.local._supports_retry and getattr(self.local, "_collective_retry", True)
+               and retries < _MAX_RETRIES):
             bad = (st_h & _RETRY_BITS).nonzero()[0]
             if bad.size == 0:
                 break
@@ -322,7 +323,11 @@ class ShardedIVFIndex(ShardedFlatIndex):
     def _make_local(self, device):
         from . import ivf
         if self.kind == 'IVF':
-            return ivf.IndexIVFFlat(self.d, self.nlist, device=device)
+            local = ivf.IndexIVFFlat(self.d, self.nlist, device=device)
+            # a flagged query of the fused list scan would need a COLLECTIVE re-run on every shard; the sharded
+            # index therefore keeps the dump path, whose exact fallback is inside the kernel
+            local.set_param("ivf_fused", 0)
+            return local
         return ivf.IndexIVFPQ(self.d, self.nlist, self.pq_m, device=device)
 
     def train(self, x, src: int = 0) -> None:

@@ -143,6 +143,25 @@ def tower():
     emit(cfg="user_tower_zipf", B=B, ms=ms_z, users_per_s=B / ms_z * 1e3)
 
 
+def ranker():
+    """Stage-2 ranker (inference.py:250-255 shape): 500 candidate rows of one user, and 64 users x 500 rows."""
+    sys.path.insert(0, str(Path(__file__).resolve().parent / "golden"))
+    from weights import RANKER_CONFIGS, feature_dims, make_ranker_inputs, make_ranker_state
+    from movie_recommender_demo_b200.transformer_ranker import TransformerRanker
+    cfg = RANKER_CONFIGS["cfg1"]
+    user, ad = feature_dims(cfg)
+    m = TransformerRanker(user, ad, cfg["numerical_dim"], embedding_dim=cfg["embedding_dim"], d_model=cfg["d_model"],
+                          num_heads=cfg["num_heads"], num_layers=cfg["num_layers"], d_ff=cfg["d_ff"])
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in make_ranker_state(cfg, 1).items()})
+    m = m.to(dev).eval()
+    per_row = 2.0 * (845 * 256 + 3 * (256 * 256 + 2 * 256 * 1024) + 3 * 256 * 256 + 3 * (256 * 256 + 256 * 64 + 64))
+    for B in (500, 32000):
+        ucat, acat, num = (torch.from_numpy(a).to(dev) for a in make_ranker_inputs(cfg, 2, B))
+        with torch.no_grad():
+            ms = timed(lambda: m(ucat, acat, num))
+        emit(cfg="stage2_ranker", rows=B, ms=ms, rows_per_s=B / ms * 1e3, TFLOPs=per_row * B / ms / 1e9)
+
+
 if __name__ == "__main__":
     what = [a for a in sys.argv[1:] if not a.startswith("--")] or ["sweep", "ivf", "ivfpq", "tower"]
     if "sweep" in what:
@@ -153,3 +172,5 @@ if __name__ == "__main__":
         ivf("IVF")
     if "ivfpq" in what:
         ivf("IVFPQ")
+    if "ranker" in what:
+        ranker()

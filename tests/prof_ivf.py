@@ -27,6 +27,10 @@ idx.add(x)
 idx.index.set_param('ivf_sample', sample)
 idx.index.set_param('ivf_debug', debug)
 idx.index.set_param('profile', 0)
+import os
+fused = int(os.environ.get('B2R_IVF_FUSED', '1'))
+if kind == 'IVF':
+    idx.index.set_param('ivf_fused', fused)
 q = torch.nn.functional.normalize(centres[torch.randint(0, nlist, (Q,), generator=g, device=dev)] + 0.35 * torch.randn((Q, 256), generator=g, device=dev), dim=1)
 for _ in range(2):
     idx.index.search_device(q, 500, normalize=True)
@@ -35,7 +39,7 @@ t0 = time.perf_counter()
 for _ in range(steps):
     idx.index.search_device(q, 500, normalize=True)
 torch.cuda.synchronize()
-print(f"debug={debug} {kind} N={N} nlist={nlist} Q={Q} sample={sample}: {(time.perf_counter() - t0) / steps * 1e3:.3f} ms/step")
+print(f"fused={fused} debug={debug} {kind} N={N} nlist={nlist} Q={Q} sample={sample}: {(time.perf_counter() - t0) / steps * 1e3:.3f} ms/step")
 import os
 if os.environ.get("PROF_TABLE"):
     from torch.profiler import profile, ProfilerActivity

@@ -143,3 +143,52 @@ def test_sampled_threshold_never_changes_the_answer(fr, kind, k):
         out[sample] = g.search(q, k=k)
         assert (g.index.last_status == 0).all()
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+@pytest.mark.parametrize("N,d,nlist,nprobe,Q,k", [(200000, 256, 256, 16, 1, 500), (200000, 256, 256, 16, 64, 500),
+                                                   (200000, 256, 256, 16, 700, 500), (50000, 128, 64, 8, 533, 100),
+                                                   (300000, 64, 128, 128, 640, 10), (9000, 256, 20, 3, 1300, 500),
+                                                   (400000, 256, 512, 32, 4096, 500)])
+def test_fused_list_scan_returns_what_the_dump_path_returns(fr, N, d, nlist, nprobe, Q, k):
+    """IVF-Flat default: sample pass -> per-query threshold -> threshold filter inside the list scan's epilogue
+    (no pair score reaches HBM; taken for chunks of 512 queries and more).  `ivf_fused = 0` dumps every pair score
+    and selects afterwards.  Same corpus, same
+    centroids: ids and scores must be identical, with no query left flagged (flagged ones are re-run through the
+    dump path by the wrapper)."""
+    import torch
+    from movie_recommender_demo_b200 import ivf
+    x = torch.from_numpy(_clustered(N, d, nlist * 2, seed=N + d))
+    q = torch.from_numpy(_clustered(Q, d, nlist * 2, seed=N + d + 1))
+    idx = ivf.IndexIVFFlat(d, nlist)
+    idx.train(x[: min(N, 64 * nlist)].cuda())
+    idx.add(x.cuda(), normalize=True)
+    out = []
+    for fused in (1, 0):
+        idx.set_param("ivf_fused", fused)
+        assert int(idx.get_param("ivf_fused")) == fused
+        D, I = idx.search(q.numpy(), k, normalize=True, nprobe=nprobe)
+        assert (idx.last_status == 0).all()
+        out.append((D, I, idx.last_retries))
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][0], out[1][0])
+    assert out[1][2] == 0
+
+
+def test_fused_list_scan_falls_back_when_the_threshold_misses(fr):
+    """k = 1000 against a candidate target of 2560: the sampled threshold can let fewer candidates through than
+    the top-k and its rescore window need for some queries; those are flagged and re-run through the dump path -
+    the answer is still the exact one."""
+    import torch
+    from movie_recommender_demo_b200 import ivf
+    N, d, nlist, nprobe, Q, k = 150000, 128, 64, 16, 600, 1000
+    x = torch.from_numpy(_clustered(N, d, 200, seed=77)).cuda()
+    q = _clustered(Q, d, 200, seed=78)
+    idx = ivf.IndexIVFFlat(d, nlist)
+    idx.train(x[:8192])
+    idx.add(x, normalize=True)
+    D1, I1 = idx.search(q, k, normalize=True, nprobe=nprobe)
+    retried, st1 = idx.last_retries, idx.last_status.copy()
+    idx.set_param("ivf_fused", 0)
+    D0, I0 = idx.search(q, k, normalize=True, nprobe=nprobe)
+    assert (st1 == 0).all() and (idx.last_status == 0).all()
+    assert np.array_equal(I1, I0) and np.array_equal(D1, D0)
+    assert retried in (0, 1)
