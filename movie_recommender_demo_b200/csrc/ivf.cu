@@ -2,7 +2,8 @@
 //
 // Replaces faiss `IndexIVFFlat(IndexFlatIP(d), d, nlist, METRIC_INNER_PRODUCT)` as built at
 // faiss_retrieval.py:50-55 and driven through .train (:93), .add (:118), .search (:155):
-//   train  : spherical k-means (IP metric), 10 iterations, <= 256 points per centroid
+//   train  : k-means with inner-product assignment, 25 iterations, <= 256 points per centroid (IVF-Flat: spherical,
+//            a documented deviation - see kKmeansIters)
 //   add    : assign each vector to the centroid of maximum inner product; append to that list
 //   search : top-nprobe centroids by inner product, exact IP over the vectors of those lists
 //
@@ -27,7 +28,12 @@
 namespace b2r {
 namespace {
 
-constexpr int kKmeansIters = 10;          // faiss ClusteringParameters.niter
+// faiss ClusteringParameters: niter = 25, max_points_per_centroid = 256, spherical = false.  Deviation:
+// the IVF-Flat centroids ARE L2-normalised after every update (spherical k-means).  The wrapper stores unit-norm
+// rows (faiss_retrieval.py:115), so argmax <c, x> with raw means favours lists whose mean happens to be long; with
+// unit centroids the assignment is the nearest direction and the lists come out balanced.  Parity never depends on
+// it: faiss's own RNG / subsampling cannot be reproduced, list membership is compared on SHARED centroids.
+constexpr int kKmeansIters = 25;
 constexpr int kMaxPointsPerCentroid = 256;  // faiss ClusteringParameters.max_points_per_centroid
 constexpr int kUnitTilesSmallQ = 8;       // corpus tiles (of 128 rows) per scan unit: few queries -> split lists for parallelism
 constexpr int kUnitTilesLargeQ = 64;      // many queries -> whole lists per unit (one query-block load per list, fewer pipeline drains)
@@ -726,40 +732,41 @@ ivf_threshold_kernel(const float* __restrict__ scorebuf, int64_t smax, const int
 // When the query scans no more rows than the candidate buffer holds, tau = -inf (everything is a candidate).
 constexpr int kIvfTauThreads = 512;
 constexpr int kIvfTauMaxKeys = 8192;
-constexpr int kIvfTauWShift = 6;     // fixed-point weights (rows per sampled row, 1/64 steps): integer histograms
+constexpr int kIvfTauWShift = 2;     // fixed-point weights (rows per sampled row, quarter-row steps): 32-bit integer histograms
 __global__ void __launch_bounds__(kIvfTauThreads)
 ivf_sample_tau_kernel(const float* __restrict__ scorebuf, int64_t smax, const int64_t* __restrict__ coarse, int nprobe,
                       const int64_t* __restrict__ list_off, int S, int c_target, int take_all_below,
                       float* __restrict__ tau) {
   extern __shared__ __align__(16) uint8_t tsm[];
+  const int max_keys = nprobe * S;                                                // <= kIvfTauMaxKeys (planner)
   uint32_t* keys = reinterpret_cast<uint32_t*>(tsm);                              // [ns] order-preserving score keys
-  uint32_t* wk = keys + kIvfTauMaxKeys;                                           // [ns] weight of each key
+  uint32_t* wk = keys + max_keys;                                                 // [ns] weight of each key
   uint32_t* wgt = wk + kIvfTauMaxKeys;                                            // [nprobe] weight of a sample of list j
   int* sstart = reinterpret_cast<int*>(wgt + nprobe);                             // [nprobe + 1] prefix of sample sizes
   int* rstart = sstart + nprobe + 1;                                              // [nprobe] run start (floats)
-  __shared__ unsigned long long hist[256];
-  __shared__ unsigned long long s_rem;
-  __shared__ uint32_t s_prefix;
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t s_rem, s_prefix;
   __shared__ int s_total_rows, s_done;
   const int q = blockIdx.x, tid = threadIdx.x;
   // list lengths: one thread per probe (the loads are two dependent round trips each - never serialise them)
   for (int j = tid; j < nprobe; j += blockDim.x) {
     const int64_t l = coarse[(size_t)q * nprobe + j];
-    rstart[j] = l >= 0 ? (int)(list_off[l + 1] - list_off[l]) : 0;
+    const int len = l >= 0 ? (int)(list_off[l + 1] - list_off[l]) : 0;
+    const int sj = len < S ? len : S;
+    rstart[j] = len;
+    wgt[j] = sj > 0 ? (uint32_t)(((uint32_t)len << kIvfTauWShift) / (uint32_t)sj) : 0u;
   }
   __syncthreads();
   if (tid == 0) {
     int64_t cum = 0, rows = 0;
     int ns = 0;
     for (int j = 0; j < nprobe; ++j) {
-      const int64_t len = rstart[j];
-      const int sj = (int)(len < S ? len : S);
+      const int len = rstart[j];
       sstart[j] = ns;
       rstart[j] = (int)cum;
-      wgt[j] = sj > 0 ? (uint32_t)((len << kIvfTauWShift) / sj) : 0u;
-      ns += sj;
+      ns += len < S ? len : S;
       rows += len;
-      cum += (len + 3) & ~(int64_t)3;
+      cum += (len + 3) & ~3;
     }
     sstart[nprobe] = ns;
     s_total_rows = (int)(rows < 0x7fffffff ? rows : 0x7fffffff);
@@ -785,7 +792,7 @@ ivf_sample_tau_kernel(const float* __restrict__ scorebuf, int64_t smax, const in
   float target = fmaxf((float)c_target, 32.f * (float)s_total_rows / (float)ns);
   target = fminf(target, (float)(take_all_below * 5 / 7));
   if (tid == 0) {
-    s_rem = (unsigned long long)((double)target * (double)(1 << kIvfTauWShift));
+    s_rem = (uint32_t)(target * (float)(1 << kIvfTauWShift));
     s_prefix = 0;
     s_done = 0;
   }
@@ -796,10 +803,10 @@ ivf_sample_tau_kernel(const float* __restrict__ scorebuf, int64_t smax, const in
   uint32_t prefix = 0, mask = 0;
   for (int pass = 0; pass < 3; ++pass) {
     const int shift = 24 - 8 * pass;
-    for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0ull;
+    for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0u;
     __syncthreads();
-    // a query's scores share their leading key bytes, so most lanes of a warp hit the SAME bin: aggregate per
-    // warp (one shared atomic per distinct bin and warp) instead of serialising thousands of atomics on one word
+    // a query's scores share their leading key bytes, so in the first pass most lanes of a warp hit the SAME bin:
+    // two warp-aggregated rounds serve the crowded bins, lanes left after that add on their own
     const int ns_pad = (ns + 31) & ~31;
     for (int i = tid; i < ns_pad; i += blockDim.x) {
       uint32_t key = 0, w = 0;
@@ -811,26 +818,46 @@ ivf_sample_tau_kernel(const float* __restrict__ scorebuf, int64_t smax, const in
       }
       const int bin = (int)((key >> shift) & 255u);
       unsigned active = __ballot_sync(0xffffffffu, on);
-      while (active) {
+#pragma unroll 1
+      for (int round = 0; round < 2 && active; ++round) {
         const int leader = __ffs(active) - 1;
         const int lbin = __shfl_sync(0xffffffffu, bin, leader);
         const bool mine = on && bin == lbin;
-        const unsigned long long sum = (unsigned long long)__reduce_add_sync(0xffffffffu, mine ? (w >> 4) : 0u) << 4;
+        const uint32_t sum = __reduce_add_sync(0xffffffffu, mine ? w : 0u);
         if ((tid & 31) == leader) atomicAdd(&hist[lbin], sum);
+        if (mine) on = false;
         active &= ~__ballot_sync(0xffffffffu, mine);
       }
+      if (on) atomicAdd(&hist[bin], w);
     }
     __syncthreads();
-    if (tid == 0) {
-      unsigned long long rem = s_rem, cum = 0;
-      int b = 255;
-      for (; b > 0; --b) {
-        if (cum + hist[b] >= rem) break;
-        cum += hist[b];
+    if (tid < 32) {          // bin where the cumulative weight from the TOP reaches s_rem (8 bins per lane)
+      const int lane = tid;
+      uint32_t part = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) part += hist[255 - (lane * 8 + b)];
+      uint32_t incl = part;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
       }
-      if (b == 0 && cum + hist[0] < rem) s_done = 1;     // the whole sample weighs less than the target: take everything
-      s_rem = rem - cum;
-      s_prefix = prefix | ((uint32_t)b << shift);
+      const uint32_t rem = s_rem;
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      __syncwarp();
+      if (total < rem) {
+        if (lane == 0) s_done = 1;       // the whole (remaining) sample weighs less than the target: take everything
+      } else if (incl >= rem && incl - part < rem) {
+        uint32_t cum = incl - part;
+        int b = 0;
+        for (; b < 7; ++b) {
+          const uint32_t hb = hist[255 - (lane * 8 + b)];
+          if (cum + hb >= rem) break;
+          cum += hb;
+        }
+        s_rem = rem - cum;
+        s_prefix = prefix | ((uint32_t)(255 - (lane * 8 + b)) << shift);
+      }
     }
     __syncthreads();
     prefix = s_prefix;
@@ -1422,10 +1449,10 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     pair_runs_kernel<<<(unsigned)ceil_div(qc, 128), 128, 0, stream>>>(coarse, qc, np, h->list_off, pl.smax, pair_out,
                                                                       row_len, listcnt);
     B2R_CHECK_LAUNCH("pair_runs_kernel");
-    // Below 512 queries a list is scanned for a handful of pairs: the dump is small, and the fused path's two
-    // extra launches (sample scan, segment gather) cost more than the score round trip saves (measured at
-    // 10M x 256, nlist 4096, nprobe 32: Q=64 0.53 vs 0.52 ms, Q=4096 2.26 vs 2.57 ms).
-    const bool fused = pl.fused && !is_pq && qc >= 512;
+    // Below ~1k queries a list is scanned for a handful of pairs: the dump is small, and the fused path's two
+    // extra launches (sample scan, segment gather) cost what the score round trip saves (measured at 10M x 256,
+    // nlist 4096, nprobe 32: Q=64 0.53 vs 0.52 ms, Q=1024 a wash, Q=4096 see DESIGN.md 3.6).
+    const bool fused = pl.fused && !is_pq && qc >= 1024;
     if (is_pq) {
       // ADC scan: one CTA per (query, probed list) pair, LUT in shared memory (ivfpq.cu)
       if ((rc = pq_scan(h, qc, npairs, q32, coarse, np, pair_out, reinterpret_cast<float*>(ws + pl.off_qtab), scorebuf,
@@ -1466,7 +1493,7 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
       ivf_scan_kernel<false><<<h->num_sms, kIvfThreads, kIvfSmem, stream>>>(tmQ, h->tmX, sp);
       B2R_CHECK_LAUNCH("ivf_scan_kernel(sample)");
       // 2. per-query threshold from the length-weighted sample
-      ivf_sample_tau_kernel<<<qc, kIvfTauThreads, (size_t)kIvfTauMaxKeys * 8 + (size_t)np * 12 + 16, stream>>>(
+      ivf_sample_tau_kernel<<<qc, kIvfTauThreads, (size_t)np * pl.sample_rows * 8 + (size_t)np * 12 + 16, stream>>>(
           scorebuf, pl.smax, coarse, np, h->list_off, pl.sample_rows, pl.c_target, pl.cap - pl.cap / 8, tau);
       B2R_CHECK_LAUNCH("ivf_sample_tau_kernel");
       // 3. the list scan with the threshold in its epilogue: only candidates leave the SM

@@ -465,6 +465,8 @@ select_rescore_kernel(const SelectParams p) {
   uint64_t* sbuf = rkeys;
   int n_sort = R;
   const int P_need = next_pow2(kk > 1 ? kk : 1);
+  // (sorting the whole ~560-key window as 1024 keys instead of cutting it down first was measured for the
+  // small-batch variant: 25.3 -> 27.6 us at Q=64, so the cut-down stays for every batch size)
   if (kk >= 1 && R > kk && P_need < next_pow2(R)) {
     const uint32_t kth_hi = radix_kth_hi(rkeys, R, kk, hist, &s_rem, &s_prefix);
     if (tid == 0) s_R = 0;

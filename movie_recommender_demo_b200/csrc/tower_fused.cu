@@ -409,17 +409,16 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
         mbar_wait(bar(FtBars::acc_full + layer), tpar, 29);
         tc_fence_after_sync();
         if (e == 0) FT_TRACE(it, 32 + layer * 2);
-#pragma unroll 1
-        for (int kc = 0; kc < KC; ++kc) {
+        // one chunk = TMEM -> +bias -> ReLU -> 16-bit -> swizzled smem -> publish.  The TMEM read of chunk kc+1 is
+        // issued before chunk kc is converted (two register buffers), so the load latency hides behind the math.
+        auto emit = [&](const uint32_t (&rr)[32], int kc) {
           const int c = kc * 2 + half;     // 32-column chunk
-          tmem_ld_32x32(tlane + (uint32_t)(c * 32), r);
-          tmem_ld_wait_dep(r);
           uint32_t pk[16];
           const float2* b2 = reinterpret_cast<const float2*>(bias.v + boff + c * 32);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float2 bb = b2[i];
-            pk[i] = pack2_relu<BF16>(__uint_as_float(r[2 * i]) + bb.x, __uint_as_float(r[2 * i + 1]) + bb.y);
+            pk[i] = pack2_relu<BF16>(__uint_as_float(rr[2 * i]) + bb.x, __uint_as_float(rr[2 * i + 1]) + bb.y);
             if (!BF16) hmax = hmax2_u32(hmax, pk[i]);
           }
           const uint32_t dst = sH + (uint32_t)(kc * kSlot);
@@ -430,6 +429,17 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
           tc_fence_before_sync();       // ... and this warp's TMEM reads are done before the MMAs overwrite the columns
           __syncwarp();
           if (lane == 0) mbar_arrive(bar((layer == 0 ? FtBars::h1_ready : FtBars::h2_ready) + kc));
+        };
+        uint32_t r2[32];
+        tmem_ld_32x32(tlane + (uint32_t)(half * 32), r);
+#pragma unroll 1
+        for (int kc = 0; kc < KC; kc += 2) {     // KC is even (widths are padded to 128 columns)
+          tmem_ld_wait_dep(r);
+          tmem_ld_32x32(tlane + (uint32_t)(((kc + 1) * 2 + half) * 32), r2);
+          emit(r, kc);
+          tmem_ld_wait_dep(r2);
+          if (kc + 2 < KC) tmem_ld_32x32(tlane + (uint32_t)(((kc + 2) * 2 + half) * 32), r);
+          emit(r2, kc + 1);
         }
         if (e == 0) FT_TRACE(it, 33 + layer * 2);
       }

@@ -146,12 +146,12 @@ def test_sampled_threshold_never_changes_the_answer(fr, kind, k):
 
 
 @pytest.mark.parametrize("N,d,nlist,nprobe,Q,k", [(200000, 256, 256, 16, 1, 500), (200000, 256, 256, 16, 64, 500),
-                                                   (200000, 256, 256, 16, 700, 500), (50000, 128, 64, 8, 533, 100),
-                                                   (300000, 64, 128, 128, 640, 10), (9000, 256, 20, 3, 1300, 500),
+                                                   (200000, 256, 256, 16, 1100, 500), (50000, 128, 64, 8, 1033, 100),
+                                                   (300000, 64, 128, 128, 1040, 10), (9000, 256, 20, 3, 1300, 500),
                                                    (400000, 256, 512, 32, 4096, 500)])
 def test_fused_list_scan_returns_what_the_dump_path_returns(fr, N, d, nlist, nprobe, Q, k):
     """IVF-Flat default: sample pass -> per-query threshold -> threshold filter inside the list scan's epilogue
-    (no pair score reaches HBM; taken for chunks of 512 queries and more).  `ivf_fused = 0` dumps every pair score
+    (no pair score reaches HBM; taken for chunks of 1024 queries and more).  `ivf_fused = 0` dumps every pair score
     and selects afterwards.  Same corpus, same
     centroids: ids and scores must be identical, with no query left flagged (flagged ones are re-run through the
     dump path by the wrapper)."""
@@ -179,7 +179,7 @@ def test_fused_list_scan_falls_back_when_the_threshold_misses(fr):
     the answer is still the exact one."""
     import torch
     from movie_recommender_demo_b200 import ivf
-    N, d, nlist, nprobe, Q, k = 150000, 128, 64, 16, 600, 1000
+    N, d, nlist, nprobe, Q, k = 150000, 128, 64, 16, 1200, 1000
     x = torch.from_numpy(_clustered(N, d, 200, seed=77)).cuda()
     q = _clustered(Q, d, 200, seed=78)
     idx = ivf.IndexIVFFlat(d, nlist)
