@@ -168,8 +168,8 @@ struct b2r_index {
   double cand_factor_fp16 = 2.5;
   int walk = 1;                  // FILTER hit walk: 1 = only the passing 3-element sub-groups (2-5 % faster), 0 = all 8
   int early_release = 0;         // filter epilogue: release the TMEM buffer before the scores are examined (A/B: no gain)
-  int pair_scan = 0;             // 1: FILTER scan of batches > 128 on CTA pairs (cta_group::2, scan_pair.cu).  Correct
-                                 // (same answers) but measured 5-10 % SLOWER than the one-CTA kernel: off by default
+  int pair_scan = 1;             // FILTER scan of batches > 128 on CTA pairs (tcgen05 cta_group::2, scan_pair.cu): 17-21 %
+                                 // faster than the one-CTA kernel (1.58 -> 1.31 ms at Q=4096); 0 selects the one-CTA kernel
   int epi_warps = 16;            // epilogue warps of the MQ = 2 filter scan (8 | 16); 16 measured 8-9 % faster
   double cand_factor = 4.0;
   int cand_cap = 4096;

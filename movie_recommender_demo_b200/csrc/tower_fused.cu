@@ -148,7 +148,11 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int j) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
 }
 
-template <bool BF16>
+// PAIR: two CTAs of a cluster (the two SMs of a TPC) run ONE tcgen05.mma.cta_group::2 stream: each CTA gathers,
+// holds and post-processes ITS OWN 128-sample tile, but a weight tile is 256 output columns of which each CTA
+// loads only its 128-row half -- half the weight bytes per sample through L2 -> SM and through the 3-slot ring
+// (the ring depth, not the tensor pipe, paces the one-CTA kernel: DESIGN.md 3.5).  Rank 0 issues the MMAs.
+template <bool BF16, bool PAIR>
 __global__ void __launch_bounds__(kFtThreads, 1)
 tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                    const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ CUtensorMap tmOut,
@@ -165,13 +169,38 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kHBytes + (kNA + kNW) * kSlot + FtBars::count * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int NT1 = p.N1p >> 7, NT2 = p.N2p >> 7, NT3 = p.N3p >> 7;
+  constexpr int kNTShift = PAIR ? 8 : 7;            // output columns per weight tile: 256 (pair) | 128
+  constexpr int kNTCols = 1 << kNTShift;
+  const int NT1 = p.N1p >> kNTShift, NT2 = p.N2p >> kNTShift, NT3 = p.N3p >> kNTShift;
   const int KC1 = p.KC1, KC2 = p.N1p >> 6, KC3 = p.N2p >> 6;
   const int tiles = (int)((p.B + 127) >> 7);
+  // work distribution: `tile0` = this CTA's first 128-sample tile, `tstep` = distance to its next one.  A pair
+  // walks tile pairs (2j, 2j + 1); both CTAs of a pair run the same number of rounds (an odd tile count leaves
+  // rank 1 an all-padding last tile: zero rows in, clipped stores out).
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) * 2 + (int)rank : (int)blockIdx.x;
+  const int tstep = PAIR ? (int)(gridDim.x >> 1) * 2 : (int)gridDim.x;
+  const int tiles_loop = PAIR ? ((tiles + 1) & ~1) : tiles;     // loop bound: `for (tile = tile0; tile < tiles_loop; tile += tstep)`
+  const bool leader = rank == 0;
+  // barriers the MMA warp waits on live in the leader; the other CTA's producers arrive remotely
+  auto lead = [&](uint32_t b) { return PAIR ? mapa_u32(b, 0) : b; };
+  auto arrive_lead = [&](uint32_t b) {
+    if (PAIR) mbar_arrive_cluster(mapa_u32(b, 0));
+    else mbar_arrive(b);
+  };
+  auto wait_lead = [&](uint32_t b, uint32_t parity, int tag) {     // leader-owned barrier with remote arrivals
+    mbar_wait(b, parity, tag);
+  };
+  auto commit = [&](uint32_t b) {
+    if (PAIR) umma_commit_pair(b);
+    else umma_commit(b);
+  };
+  (void)lead;
 
   if (warp == 1 && lane == 0) {
+    constexpr int kCtas = PAIR ? 2 : 1;      // arrivals of both CTAs land on the leader's barriers
     for (int i = 0; i < kNA; ++i) {
-      mbar_init(bar(FtBars::a_full + i), kFtGatherWarps);
+      mbar_init(bar(FtBars::a_full + i), kFtGatherWarps * kCtas);
       mbar_init(bar(FtBars::a_empty + i), 1);
     }
     for (int i = 0; i < kNW; ++i) {
@@ -179,12 +208,15 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       mbar_init(bar(FtBars::w_empty + i), 1);
     }
     for (int i = 0; i < 3; ++i) mbar_init(bar(FtBars::acc_full + i), 1);
-    for (int i = 0; i < kMaxKC; ++i) mbar_init(bar(FtBars::h1_ready + i), kFtEpiWarps);
-    for (int i = 0; i < kMaxKC / 2; ++i) mbar_init(bar(FtBars::h2_ready + i), kFtEpiWarps);
-    mbar_init(bar(FtBars::tmem_free), kFtEpiWarps);
+    for (int i = 0; i < kMaxKC; ++i) mbar_init(bar(FtBars::h1_ready + i), kFtEpiWarps * kCtas);
+    for (int i = 0; i < kMaxKC / 2; ++i) mbar_init(bar(FtBars::h2_ready + i), kFtEpiWarps * kCtas);
+    mbar_init(bar(FtBars::tmem_free), kFtEpiWarps * kCtas);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<512>(smem_u32(tmem_slot));
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_pair(smem_u32(tmem_slot));
+    else tmem_alloc<512>(smem_u32(tmem_slot));
+  }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmW1);
     prefetch_tmap(&tmW2);
@@ -192,7 +224,8 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     prefetch_tmap(&tmOut);
   }
   tc_fence_before_sync();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();     // barriers initialised and TMEM allocated in both CTAs before any remote access
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -203,11 +236,17 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       uint32_t ph = 0;
       auto put = [&](const CUtensorMap* tm, int kc, int nt) {
         mbar_wait(bar(FtBars::w_empty + slot), ph ^ 1, 21);
-        mbar_arrive_expect_tx(bar(FtBars::w_full + slot), (uint32_t)kSlot);
-        tma_load_2d(sW + slot * kSlot, tm, kc * 64, nt * 128, bar(FtBars::w_full + slot));
+        if (PAIR) {
+          // both CTAs load their 128-row half of the 256-column weight tile; the bytes of both land on the leader's barrier
+          if (leader) mbar_arrive_expect_tx(bar(FtBars::w_full + slot), (uint32_t)(2 * kSlot));
+          tma_load_2d_pair(sW + slot * kSlot, tm, kc * 64, nt * kNTCols + (int)rank * 128, lead(bar(FtBars::w_full + slot)));
+        } else {
+          mbar_arrive_expect_tx(bar(FtBars::w_full + slot), (uint32_t)kSlot);
+          tma_load_2d(sW + slot * kSlot, tm, kc * 64, nt * 128, bar(FtBars::w_full + slot));
+        }
         if (++slot == kNW) { slot = 0; ph ^= 1; }
       };
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < tiles_loop; tile += tstep) {
         for (int kc = 0; kc < KC1; ++kc)
           for (int nt = 0; nt < NT1; ++nt) put(&tmW1, kc, nt);
         for (int kc = 0; kc < KC2; ++kc)
@@ -216,9 +255,10 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
           for (int nt = 0; nt < NT3; ++nt) put(&tmW3, kc, nt);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && leader) {
     // ============================================================ MMA issuer (warp-uniform loop, one elected lane issues)
-    constexpr uint32_t idesc = BF16 ? umma_idesc_bf16_f32(128, 128) : umma_idesc_f16_f32(128, 128);
+    constexpr int kMmaM = PAIR ? 256 : 128;     // pair: M = 128 rows of each CTA, N = 256 = 128 weight rows of each CTA
+    constexpr uint32_t idesc = BF16 ? umma_idesc_bf16_f32(kMmaM, kNTCols) : umma_idesc_f16_f32(kMmaM, kNTCols);
     const uint64_t descH = umma_desc_kmajor_sw128(sH);
     const uint64_t descA = umma_desc_kmajor_sw128(sA);
     const uint64_t descW = umma_desc_kmajor_sw128(sW);
@@ -231,61 +271,63 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
         tc_fence_after_sync();
         if (elect_one()) {
           const uint64_t bd = descW + (uint64_t)((ws * kSlot) >> 4);
-          const uint32_t d_tmem = tmem_base + acc_col + (uint32_t)(nt * 128);
+          const uint32_t d_tmem = tmem_base + acc_col + (uint32_t)(nt * kNTCols);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(d_tmem, adesc + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (uint32_t)(!first || k != 0));
-          umma_commit(bar(FtBars::w_empty + ws));
+          for (int k = 0; k < 4; ++k) {
+            if (PAIR) umma_pair_ss(d_tmem, adesc + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (uint32_t)(!first || k != 0));
+            else umma_bf16_ss(d_tmem, adesc + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (uint32_t)(!first || k != 0));
+          }
+          commit(bar(FtBars::w_empty + ws));
         }
         __syncwarp();
         if (++ws == kNW) { ws = 0; wph ^= 1; }
       }
     };
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < tiles_loop; tile += tstep, ++it) {
       const uint32_t tpar = it & 1;
       // the previous tile's epilogues 2 and 3 must have drained their accumulators before GEMM1 overwrites them
       FT_TRACE(it, 0);
-      mbar_wait(bar(FtBars::tmem_free), tpar ^ 1, 23);
+      wait_lead(bar(FtBars::tmem_free), tpar ^ 1, 23);
       tc_fence_after_sync();
       FT_TRACE(it, 1);
       for (int kc = 0; kc < KC1; ++kc) {
-        mbar_wait(bar(FtBars::a_full + as), aph, 24);
+        wait_lead(bar(FtBars::a_full + as), aph, 24);
         tc_fence_after_sync();
         if (kc < 8) FT_TRACE(it, 2 + kc);
         chunk(descA + (uint64_t)((as * kSlot) >> 4), NT1, 0u, kc == 0);
-        if (elect_one()) umma_commit(bar(FtBars::a_empty + as));
+        if (elect_one()) commit(bar(FtBars::a_empty + as));
         __syncwarp();
         if (++as == kNA) { as = 0; aph ^= 1; }
       }
-      if (elect_one()) umma_commit(bar(FtBars::acc_full + 0));
+      if (elect_one()) commit(bar(FtBars::acc_full + 0));
       __syncwarp();
       FT_TRACE(it, 10);
       // GEMM2 accumulates into columns [0, N2p): those must have been drained by epilogue 1, i.e. the H1
       // chunks that came out of them are complete
-      for (int kc = 0; kc < KC3 && kc < KC2; ++kc) mbar_wait(bar(FtBars::h1_ready + kc), tpar, 25);
+      for (int kc = 0; kc < KC3 && kc < KC2; ++kc) wait_lead(bar(FtBars::h1_ready + kc), tpar, 25);
       FT_TRACE(it, 11);
       for (int kc = 0; kc < KC2; ++kc) {
-        mbar_wait(bar(FtBars::h1_ready + kc), tpar, 26);
+        wait_lead(bar(FtBars::h1_ready + kc), tpar, 26);
         tc_fence_after_sync();
         chunk(descH + (uint64_t)((kc * kSlot) >> 4), NT2, 0u, kc == 0);
       }
-      if (elect_one()) umma_commit(bar(FtBars::acc_full + 1));
+      if (elect_one()) commit(bar(FtBars::acc_full + 1));
       __syncwarp();
       FT_TRACE(it, 12);
       for (int kc = 0; kc < KC3; ++kc) {
-        mbar_wait(bar(FtBars::h2_ready + kc), tpar, 27);
+        wait_lead(bar(FtBars::h2_ready + kc), tpar, 27);
         tc_fence_after_sync();
         chunk(descH + (uint64_t)((kc * kSlot) >> 4), NT3, 256u, kc == 0);
       }
-      if (elect_one()) umma_commit(bar(FtBars::acc_full + 2));
+      if (elect_one()) commit(bar(FtBars::acc_full + 2));
       __syncwarp();
       FT_TRACE(it, 13);
     }
   } else if (warp == 3) {
     // ============================================================ L2 prefetch of the NEXT tile's ids (contiguous block)
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const int64_t nrow0 = ((int64_t)tile + gridDim.x) * 128;
+    for (int tile = tile0; tile < tiles_loop; tile += tstep) {
+      const int64_t nrow0 = ((int64_t)tile + tstep) * 128;
       if (nrow0 < p.B) {
         const int64_t rows = (p.B - nrow0) < 128 ? (p.B - nrow0) : 128;
         const char* c0 = reinterpret_cast<const char*>(p.cat + nrow0 * p.F);
@@ -309,7 +351,7 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     const int piece = t & 15;                             // 4-float piece of the 64-column chunk
     const int rsub = t >> 4;                              // rows rsub, rsub + 16, ...
     const int FE4 = p.F * p.E4;
-    const int my_tiles = tiles > (int)blockIdx.x ? (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int my_tiles = tiles_loop > tile0 ? (tiles_loop - tile0 + tstep - 1) / tstep : 0;
     const int items = my_tiles * KC1;                     // (tile, chunk) pairs this CTA gathers, in order
     int slot = 0;
     uint32_t ph = 0;
@@ -327,7 +369,7 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       const int f = emb ? w4 / p.E4 : 0;
       o.tab = reinterpret_cast<const float4*>(p.tables[f]) + (emb ? w4 - f * p.E4 : 0);
       o.card = __ldg(p.cards + f);
-      const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)(n / KC1) * gridDim.x) * 128;
+      const int64_t row0 = ((int64_t)tile0 + (int64_t)(n / KC1) * tstep) * 128;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int64_t grow = row0 + i * 16 + rsub;
@@ -339,7 +381,7 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     for (int n = 0; n < items; ++n) {
       const int kc = n % KC1;
       const uint32_t git = (uint32_t)(n / KC1);
-      const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)git * gridDim.x) * 128;
+      const int64_t row0 = ((int64_t)tile0 + (int64_t)git * tstep) * 128;
       if (warp == kFtGatherWarp0 && kc < 8) FT_TRACE(git, 16 + kc);
       const int w4 = kc * 16 + piece;
       float4 v[8];
@@ -381,7 +423,7 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(FtBars::a_full + slot));
+      if (lane == 0) arrive_lead(bar(FtBars::a_full + slot));
       if (warp == kFtGatherWarp0 && kc < 8) FT_TRACE(git, 24 + kc);
       if (++slot == kNA) { slot = 0; ph ^= 1; }
     }
@@ -399,7 +441,7 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     float* ssx = reinterpret_cast<float*>(smem);               // [8][32] partial sums of squares (H chunk 0, free in epilogue 3)
     uint32_t hmax = 0u;      // running max of the packed fp16 activations (>= 0 after ReLU): 0x7BFF = saturated
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < tiles_loop; tile += tstep, ++it) {
       const uint32_t tpar = it & 1;
       uint32_t r[32];
       // ---- hidden layers: TMEM -> bias -> ReLU -> 16-bit -> swizzled K-major chunk of the next layer's A operand
@@ -428,7 +470,7 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
           fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core's async-proxy reads
           tc_fence_before_sync();       // ... and this warp's TMEM reads are done before the MMAs overwrite the columns
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar((layer == 0 ? FtBars::h1_ready : FtBars::h2_ready) + kc));
+          if (lane == 0) arrive_lead(bar((layer == 0 ? FtBars::h1_ready : FtBars::h2_ready) + kc));
         };
         uint32_t r2[32];
         tmem_ld_32x32(tlane + (uint32_t)(half * 32), r);
@@ -475,7 +517,7 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
         if (kc + 1 == (p.N3p >> 6)) {     // last TMEM read of this tile by this warp: release the accumulators
           tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar(FtBars::tmem_free));
+          if (lane == 0) arrive_lead(bar(FtBars::tmem_free));
         }
         if (lane == 0) bulk_wait_read<1>();       // the store that last used this staging buffer has read it
         __syncwarp();
@@ -512,10 +554,12 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
   }
   __syncwarp();
   tc_fence_before_sync();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // neither CTA may leave (or free TMEM) while the pair's MMAs / remote arrives are in flight
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after_sync();
-    tmem_dealloc<512>(tmem_base);
+    if (PAIR) tmem_dealloc_pair(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -573,20 +617,42 @@ int launch_tower_fused(b2r_tower* t, const int64_t* cat, const float* num, int64
   p.N3p = t->np[2];
   p.err_flag = err_flag;
   p.trace = reinterpret_cast<long long*>(t->trace_ptr);
-  static bool configured[2][64] = {};
   int dev = 0;
   B2R_CUDA(cudaGetDevice(&dev));
   const int bf = t->bf16 ? 1 : 0;
-  if (!configured[bf][dev & 63]) {
-    if (bf) B2R_CUDA(cudaFuncSetAttribute(tower_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmem));
-    else B2R_CUDA(cudaFuncSetAttribute(tower_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmem));
-    configured[bf][dev & 63] = true;
-  }
   const int64_t tiles = (B + 127) / 128;
-  const int grid = (int)(tiles < t->num_sms ? tiles : t->num_sms);
   const FtBias& bias = *reinterpret_cast<const FtBias*>(t->bias_host);
-  if (bf) tower_fused_kernel<true><<<grid, kFtThreads, kFtSmem, stream>>>(t->tmWfb[0], t->tmWfb[1], t->tmWfb[2], tmOut, bias, p);
-  else tower_fused_kernel<false><<<grid, kFtThreads, kFtSmem, stream>>>(t->tmWf[0], t->tmWf[1], t->tmWf[2], tmOut, bias, p);
+  // CTA pairs (cta_group::2): weight tiles of 256 columns -> every padded width must be a multiple of 256
+  const bool pair = t->pair && t->num_sms >= 2 && tiles >= 2 && (p.N1p % 256) == 0 && (p.N2p % 256) == 0 && (p.N3p % 256) == 0;
+  static bool configured[2][2][64] = {};
+  if (!configured[pair][bf][dev & 63]) {
+    const void* fn = pair ? (bf ? (const void*)tower_fused_kernel<true, true> : (const void*)tower_fused_kernel<false, true>)
+                          : (bf ? (const void*)tower_fused_kernel<true, false> : (const void*)tower_fused_kernel<false, false>);
+    B2R_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmem));
+    configured[pair][bf][dev & 63] = true;
+  }
+  if (pair) {
+    const int64_t pairs = (tiles + 1) / 2;
+    const int clusters = (int)(pairs < t->num_sms / 2 ? pairs : t->num_sms / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kFtThreads);
+    cfg.dynamicSmemBytes = kFtSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (bf) B2R_CUDA(cudaLaunchKernelEx(&cfg, tower_fused_kernel<true, true>, t->tmWfb[0], t->tmWfb[1], t->tmWfb[2], tmOut, bias, p));
+    else B2R_CUDA(cudaLaunchKernelEx(&cfg, tower_fused_kernel<false, true>, t->tmWf[0], t->tmWf[1], t->tmWf[2], tmOut, bias, p));
+  } else {
+    const int grid = (int)(tiles < t->num_sms ? tiles : t->num_sms);
+    if (bf) tower_fused_kernel<true, false><<<grid, kFtThreads, kFtSmem, stream>>>(t->tmWfb[0], t->tmWfb[1], t->tmWfb[2], tmOut, bias, p);
+    else tower_fused_kernel<false, false><<<grid, kFtThreads, kFtSmem, stream>>>(t->tmWf[0], t->tmWf[1], t->tmWf[2], tmOut, bias, p);
+  }
   B2R_CHECK_LAUNCH("tower_fused_kernel");
   return B2R_OK;
 }

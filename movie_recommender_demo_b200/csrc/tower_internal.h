@@ -16,6 +16,8 @@ struct b2r_tower {
   // the fp16 range).  Both weight copies are kept so the switch costs nothing at run time.
   int bf16 = 0;
   int force_path = 0;            // 0 auto, 1 layer-by-layer kernels, 2 fused kernel (tests)
+  int pair = 1;                  // fused kernel on CTA pairs (tcgen05 cta_group::2, 256-column weight tiles) when every padded
+                                 // width is a multiple of 256: 0.148 -> 0.139 ms at B = 65536; set_param("pair", 0) = one CTA per tile
   uintptr_t trace_ptr = 0;       // debug: device buffer for the fused kernel's phase timeline (tests/prof_tower.py)
   __half* w[3] = {nullptr, nullptr, nullptr};          // [np[l], Kp[l]] fp16, zero padded
   __nv_bfloat16* wb[3] = {nullptr, nullptr, nullptr};  // the same weights in bf16

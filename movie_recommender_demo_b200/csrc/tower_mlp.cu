@@ -570,6 +570,8 @@ int b2r_tower_set_param(b2r_tower* t, const char* name, double value) {
     t->bf16 = (int)value;
   } else if (n == "trace_ptr") {      // debug: device pointer (as a double; < 2^53) of a [4][8][64] int64 buffer, 0 = off
     t->trace_ptr = (uintptr_t)value;
+  } else if (n == "pair") {           // fused kernel: 1 = CTA pairs (cta_group::2), 0 = one CTA per tile
+    t->pair = value != 0;
   } else if (n == "force_path") {     // 0 auto | 1 layer-by-layer | 2 fused
     if (value == 2 && !t->fused_ok) return fail(B2R_EUNSUPPORTED, "this tower's shape does not fit the fused kernel");
     t->force_path = (int)value;
@@ -584,6 +586,7 @@ double b2r_tower_get_param(const b2r_tower* t, const char* name) {
   const std::string n(name);
   if (n == "operand_dtype") return t->bf16;
   if (n == "force_path") return t->force_path;
+  if (n == "pair") return t->pair;
   if (n == "fused") return (t->force_path == 2 || (t->force_path == 0 && t->fused_ok)) ? 1 : 0;
   return NAN;
 }

@@ -176,6 +176,7 @@ class _Tower(nn.Module):
     sync_checks = None    # see _DeviceFlags: None = synchronous check on the first forward after (re)loading weights
     operand_dtype = None  # None: fp16 operands, bf16 once a saturation is seen; "fp16" / "bf16" pin the format
     force_path = 0        # tests: 1 = layer-by-layer kernels, 2 = fused kernel
+    pair = None           # fused kernel on CTA pairs (tcgen05 cta_group::2): None = library default, 0 / 1 force
 
     def _build(self, feature_dims: Dict[str, int], numerical_dim: int, embedding_dim: int,
                hidden_dims: List[int], output_dim: int, dropout: float) -> None:
@@ -237,6 +238,8 @@ class _Tower(nn.Module):
                 _lib.check(lib.b2r_tower_set_param(h, b"operand_dtype", {"fp16": 0.0, "bf16": 1.0}[self.operand_dtype]))
             if self.force_path:
                 _lib.check(lib.b2r_tower_set_param(h, b"force_path", float(self.force_path)))
+            if self.pair is not None:
+                _lib.check(lib.b2r_tower_set_param(h, b"pair", float(self.pair)))
         self._handle, self._handle_sig = h, sig
         self._flags = _DeviceFlags(device)
         self._fresh = True

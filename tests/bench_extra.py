@@ -130,6 +130,14 @@ def tower():
     g = torch.Generator(device=dev).manual_seed(6)
     cat = torch.randint(0, rows, (B, 26), generator=g, device=dev)
     num = torch.randn((B, 13), generator=g, device=dev)
+    for a in sys.argv:                       # A/B of the fused kernel on CTA pairs: --pair=0,1,0,1
+        if a.startswith("--pair="):
+            for mode in a.split("=")[1].split(","):
+                t.pair = int(mode)
+                t._free()
+                emit(cfg="user_tower_pair_ab", pair=int(mode), ms=timed(lambda: t(cat, num)))
+            t.pair = None
+            t._free()
     ms = timed(lambda: t(cat, num))
     ms_g = timed(lambda: t.embedding_layer(cat))
     flops = 2.0 * B * (429 * 512 + 512 * 256 + 256 * 256)

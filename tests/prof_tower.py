@@ -14,6 +14,8 @@ rows = 1_000_000 if "--small" in sys.argv else 10_000_000
 dev = torch.device("cuda")
 torch.manual_seed(5)
 t = UserTower({f"C{i + 1}": rows for i in range(26)}, 13).to(dev).eval()
+if "--pair" in sys.argv:
+    t.pair = 1
 B = 65536
 g = torch.Generator(device=dev).manual_seed(6)
 cat = torch.randint(0, rows, (B, 26), generator=g, device=dev)

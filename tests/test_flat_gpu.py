@@ -176,8 +176,8 @@ def test_two_query_block_filter_scan_both_epilogue_layouts(fr, N, Q, k, d, epi_w
 @pytest.mark.parametrize("N,Q,k,d", [(400000, 300, 500, 256), (250000, 1000, 100, 128), (999999, 257, 500, 64),
                                      (300001, 129, 500, 192), (65000, 600, 500, 256)])
 def test_cta_pair_filter_scan_matches_oracle(fr, N, Q, k, d, pair_scan):
-    """`pair_scan = 1` runs the filter scan of batches above 128 queries on CTA pairs (tcgen05 cta_group::2: 256
-    queries x 256 corpus rows per UMMA, scan_pair.cu); 0 (default) is the one-CTA kernel.  Both give the oracle's answer
+    """`pair_scan = 1` (default) runs the filter scan of batches above 128 queries on CTA pairs (tcgen05 cta_group::2:
+    256 queries x 256 corpus rows per UMMA, scan_pair.cu); 0 is the one-CTA kernel.  Both give the oracle's answer
     (odd corpus sizes: the last pair tile is half or partly empty; Q = 129 / 257: an all-padding second block)."""
     _parity(fr, N, Q, k, d=d, seed=N + Q, pair_scan=pair_scan)
 

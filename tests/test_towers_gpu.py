@@ -208,3 +208,33 @@ def test_index_check_is_deferred_after_the_first_forward(built_lib):
     emb(torch.from_numpy(bad).cuda())
     with pytest.raises(IndexError):
         emb.check()
+
+
+@pytest.mark.parametrize("B", [1, 128, 129, 255, 257, 1000, 20000, 65536])
+def test_fused_tower_on_cta_pairs_matches_the_one_cta_kernel(built_lib, B):
+    """`pair = 1`: two CTAs of a cluster drive one tcgen05.mma.cta_group::2 stream (256-column weight tiles, each
+    CTA loads half of every tile; an odd tile count leaves rank 1 an all-padding tile).  Same arithmetic as the
+    one-CTA fused kernel: equal within fp32 summation-order noise, and within tolerance of the fp32 oracle."""
+    import torch
+    from oracle import towers as otowers
+    from weights import make_inputs
+    m, fx, cfg, state = _model("cfg1")
+    ucat, unum, acat = make_inputs(cfg, 7 + B, B)
+    outs = {}
+    for pair in (0, 1):
+        for tower in (m.user_tower, m.ad_tower):
+            tower.force_path = 2
+            tower.pair = pair
+            tower._free()
+        with torch.no_grad():
+            u = m.get_user_embeddings(torch.from_numpy(ucat).cuda(), torch.from_numpy(unum).cuda()).cpu().numpy()
+            a = m.get_ad_embeddings(torch.from_numpy(acat).cuda()).cpu().numpy()
+        assert built_lib.b2r_tower_get_param(m.user_tower._handle, b"pair") == float(pair)
+        outs[pair] = (u, a)
+    n_ref = min(B, 1000)
+    ref_u = otowers.tower_forward(state, "user_tower", ucat[:n_ref], unum[:n_ref])
+    ref_a = otowers.tower_forward(state, "ad_tower", acat[:n_ref])
+    assert np.abs(outs[1][0][:n_ref] - ref_u).max() < TOWER_ATOL
+    assert np.abs(outs[1][1][:n_ref] - ref_a).max() < TOWER_ATOL
+    assert np.abs(outs[0][0] - outs[1][0]).max() < 2e-6
+    assert np.abs(outs[0][1] - outs[1][1]).max() < 2e-6
