@@ -741,7 +741,7 @@ ivf_sample_tau_kernel(const float* __restrict__ scorebuf, int64_t smax, const in
   const int max_keys = nprobe * S;                                                // <= kIvfTauMaxKeys (planner)
   uint32_t* keys = reinterpret_cast<uint32_t*>(tsm);                              // [ns] order-preserving score keys
   uint32_t* wk = keys + max_keys;                                                 // [ns] weight of each key
-  uint32_t* wgt = wk + kIvfTauMaxKeys;                                            // [nprobe] weight of a sample of list j
+  uint32_t* wgt = wk + max_keys;                                                  // [nprobe] weight of a sample of list j
   int* sstart = reinterpret_cast<int*>(wgt + nprobe);                             // [nprobe + 1] prefix of sample sizes
   int* rstart = sstart + nprobe + 1;                                              // [nprobe] run start (floats)
   __shared__ uint32_t hist[256];

@@ -451,8 +451,8 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
         mbar_wait(bar(FtBars::acc_full + layer), tpar, 29);
         tc_fence_after_sync();
         if (e == 0) FT_TRACE(it, 32 + layer * 2);
-        // one chunk = TMEM -> +bias -> ReLU -> 16-bit -> swizzled smem -> publish.  The TMEM read of chunk kc+1 is
-        // issued before chunk kc is converted (two register buffers), so the load latency hides behind the math.
+        // one chunk = TMEM -> +bias -> ReLU -> 16-bit -> swizzled smem.  The TMEM read of chunk kc+1 is issued
+        // before chunk kc is converted (two register buffers), so the load latency hides behind the math.
         auto emit = [&](const uint32_t (&rr)[32], int kc) {
           const int c = kc * 2 + half;     // 32-column chunk
           uint32_t pk[16];
@@ -467,13 +467,22 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             st_shared_v4(dst + sw128_off(row, half * 4 + j), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        };
+        // publish chunks [k0, k1): ONE proxy fence for the group (the fence, not the math, was the cost of a chunk:
+        // ~1.6 k cycles each in the phase trace), then one arrive per chunk barrier
+        auto publish = [&](int k0, int k1) {
           fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core's async-proxy reads
           tc_fence_before_sync();       // ... and this warp's TMEM reads are done before the MMAs overwrite the columns
           __syncwarp();
-          if (lane == 0) arrive_lead(bar((layer == 0 ? FtBars::h1_ready : FtBars::h2_ready) + kc));
+          if (lane == 0)
+            for (int kc = k0; kc < k1; ++kc) arrive_lead(bar((layer == 0 ? FtBars::h1_ready : FtBars::h2_ready) + kc));
         };
+        // Layer 1: GEMM2 re-uses the TMEM columns of H1's first N2p columns, so it cannot start before chunks
+        // [0, KC3) are ALL drained: they are published as one group.  Later chunks go out in pairs.
+        const int first_group = layer == 0 ? ((KC3 < KC ? KC3 : KC) + 1) & ~1 : 2;
         uint32_t r2[32];
         tmem_ld_32x32(tlane + (uint32_t)(half * 32), r);
+        int pub = 0;
 #pragma unroll 1
         for (int kc = 0; kc < KC; kc += 2) {     // KC is even (widths are padded to 128 columns)
           tmem_ld_wait_dep(r);
@@ -482,6 +491,10 @@ tower_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
           tmem_ld_wait_dep(r2);
           if (kc + 2 < KC) tmem_ld_32x32(tlane + (uint32_t)(((kc + 2) * 2 + half) * 32), r);
           emit(r2, kc + 1);
+          if (kc + 2 >= first_group || kc + 2 >= KC) {
+            publish(pub, kc + 2);
+            pub = kc + 2;
+          }
         }
         if (e == 0) FT_TRACE(it, 33 + layer * 2);
       }
