@@ -647,7 +647,9 @@ def run_b200(args):
             roof["note"] = ("above 1.0: the kernel only READS the corpus; the measured peak is a copy (read + write) "
                             "bandwidth, which a pure read stream exceeds on long launches")
     traffic = _traffic_note(Q) if n_shard == CORPUS_1GPU else None
-    roof.update({"kernel": "scan_tc_kernel<MQ,FILTER> (tcgen05 score contraction + threshold filter)",
+    pair = Q > 128 and int(flat.get_param("pair_scan")) == 1
+    roof.update({"kernel": ("scan_pair_kernel (tcgen05 cta_group::2 score contraction on CTA pairs + threshold filter)" if pair
+                            else "scan_tc_kernel<MQ,FILTER> (tcgen05 score contraction + threshold filter)"),
                  "kernel_ms": scan_ms, "traffic": traffic,
                  "traffic_source": ("dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this "
                                     "kernel at this batch (profiles/traffic.json); not measured in this run") if traffic else None})

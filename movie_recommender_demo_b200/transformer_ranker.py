@@ -119,6 +119,8 @@ class TransformerRanker(nn.Module):
         self._ws = None
         self._tensors = None
         self._fresh = True
+        self._graphs = None
+        self._graphs_for = None
 
     # -- native handle, rebuilt whenever a parameter changes (same scheme as the towers) ---------------
     def _signature(self, device):
@@ -165,6 +167,7 @@ class TransformerRanker(nn.Module):
 
     def _free(self):
         self._tensors = None
+        self._graphs = None
         if getattr(self, "_handle", None) is not None:
             try:
                 _lib.load().b2r_ranker_destroy(self._handle)
@@ -220,23 +223,68 @@ class TransformerRanker(nn.Module):
             raise RuntimeError("TransformerRanker.forward: inconsistent batch / feature shapes")
         h = self._native(dev)
         T = len(self.prediction_heads)
-        out = torch.empty((T, B), dtype=torch.float32, device=dev)
-        if B > 0:
-            need = int(lib.b2r_ranker_workspace(h, B))
-            if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
-                self._ws = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            for attempt in range(2):
-                with torch.cuda.device(dev):
-                    _lib.check(lib.b2r_ranker_forward(h, ucat.data_ptr(), acat.data_ptr(), num.data_ptr(), B,
-                                                      out.data_ptr(), self._flags.dev.data_ptr(), self._ws.data_ptr(),
-                                                      self._ws.numel(), stream))
-                self._flags.publish()
-                # the ranker runs once per request on 500 rows: a synchronous status check costs nothing next to
-                # the D2H copy of the scores that follows (inference.py:258-260)
-                if not self._react(self._flags.poll(wait=True)):
-                    break
+        if B == 0:
+            out = torch.empty((T, 0), dtype=torch.float32, device=dev)
+            return {t: out[i] for i, t in enumerate(self.prediction_heads)}
+        for attempt in range(2):
+            out = self._launch(h, dev, ucat, acat, num, B, T)
+            self._flags.publish()
+            # the ranker runs once per request on 500 rows: a synchronous status check costs nothing next to
+            # the D2H copy of the scores that follows (inference.py:258-260)
+            if not self._react(self._flags.poll(wait=True)):
+                break
+            self._graphs = {}          # operand format changed: the captured launch sequences are stale
         return {t: out[i] for i, t in enumerate(self.prediction_heads)}
+
+    # The forward is ~30 short launches (15 GEMMs + row kernels); at the 500 rows of one user they are launch-bound
+    # (0.28 ms eager).  For batches up to _GRAPH_MAX_ROWS the sequence is captured once per batch size into a CUDA
+    # graph over static input / output / workspace buffers and replayed (B2R_NO_GRAPHS=1 disables).
+    _GRAPH_MAX_ROWS = 4096
+
+    def _launch(self, h, dev, ucat, acat, num, B, T):
+        import os
+        lib = _lib.load()
+
+        def run(uc, ac, nm, out, ws):
+            with torch.cuda.device(dev):
+                _lib.check(lib.b2r_ranker_forward(h, uc.data_ptr(), ac.data_ptr(), nm.data_ptr(), B, out.data_ptr(),
+                                                  self._flags.dev.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                  torch.cuda.current_stream(dev).cuda_stream))
+
+        need = int(lib.b2r_ranker_workspace(h, B))
+        if B <= self._GRAPH_MAX_ROWS and not os.environ.get("B2R_NO_GRAPHS"):
+            if getattr(self, "_graphs", None) is None or getattr(self, "_graphs_for", None) is not h:
+                self._graphs, self._graphs_for = {}, h
+            ent = self._graphs.get(B)
+            if ent is None:
+                ent = {"uc": torch.zeros_like(ucat), "ac": torch.zeros_like(acat), "nm": torch.zeros_like(num),
+                       "out": torch.empty((T, B), dtype=torch.float32, device=dev),
+                       "ws": torch.empty(max(need, 1), dtype=torch.uint8, device=dev)}
+                try:
+                    run(ent["uc"], ent["ac"], ent["nm"], ent["out"], ent["ws"])    # eager once: kernel attributes
+                    torch.cuda.synchronize(dev)
+                    self._flags.dev.zero_()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        run(ent["uc"], ent["ac"], ent["nm"], ent["out"], ent["ws"])
+                    ent["graph"] = g
+                except Exception as exc:   # not capturable here: stay eager for this batch size
+                    import warnings
+                    warnings.warn(f"TransformerRanker: CUDA-graph capture failed ({type(exc).__name__}: {exc}); staying eager")
+                    torch.cuda.synchronize(dev)
+                    ent = False
+                self._graphs[B] = ent
+            if ent:
+                ent["uc"].copy_(ucat, non_blocking=True)
+                ent["ac"].copy_(acat, non_blocking=True)
+                ent["nm"].copy_(num, non_blocking=True)
+                ent["graph"].replay()
+                return ent["out"].clone()
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+        out = torch.empty((T, B), dtype=torch.float32, device=dev)
+        run(ucat, acat, num, out, self._ws)
+        return out
 
     def compute_loss(self, *a, **k):
         raise NotImplementedError("training is out of scope of the B200 inference path (reference :382-420)")
