@@ -23,20 +23,38 @@ def build_faiss_index(model, ad_data, device: str, save_path: str = None, batch_
     say = print if FAISSIndex.verbose else (lambda *a, **k: None)
     say("\n=== Building FAISS Index ===")
     model = model.to(device).eval()
-    chunks = []
     if isinstance(ad_data, torch.utils.data.Dataset):
         loader = torch.utils.data.DataLoader(ad_data, batch_size=batch_size, shuffle=False)
         batches = (b['ad_categorical'] for b in loader)
+        total = len(ad_data)
     else:
         feats = torch.as_tensor(ad_data)
         batches = (feats[i:i + batch_size] for i in range(0, len(feats), batch_size))
+        total = len(feats)
+    d = model.output_dim
+    index = FAISSIndex(dimension=d, index_type=index_type, nlist=nlist, nprobe=nprobe)
+    done = 0
     with torch.no_grad():
-        for ad_cat in batches:
-            chunks.append(model.get_ad_embeddings(ad_cat.to(device)))
-    ad_embeddings = torch.cat(chunks) if chunks else torch.zeros((0, model.output_dim), device=device)
-    say(f"Generated {len(ad_embeddings)} ad embeddings")
-    index = FAISSIndex(dimension=ad_embeddings.shape[1], index_type=index_type, nlist=nlist, nprobe=nprobe)
-    index.add(ad_embeddings, list(range(len(ad_embeddings))))
+        if index_type == 'Flat':
+            # a flat index needs no training: every batch goes from the tower kernels straight into the index's
+            # pre-sized corpus buffers (fp32 master + 16-bit scan copy) - no intermediate embedding matrix at all
+            index.index.reserve(total)
+            for ad_cat in batches:
+                emb = model.get_ad_embeddings(ad_cat.to(device))
+                index.add(emb, list(range(done, done + len(emb))))
+                done += len(emb)
+        else:
+            # IVF types train on the embeddings of the first add (faiss_retrieval.py:107-108): the reference hands
+            # ALL rows to that one call, so they are collected first - in ONE pre-sized device tensor (a list of
+            # chunks + torch.cat would hold the corpus twice)
+            ad_embeddings = torch.empty((total, d), dtype=torch.float32, device=device)
+            for ad_cat in batches:
+                emb = model.get_ad_embeddings(ad_cat.to(device))
+                ad_embeddings[done:done + len(emb)].copy_(emb)
+                done += len(emb)
+            index.add(ad_embeddings[:done], list(range(done)))
+            del ad_embeddings
+    say(f"Generated {done} ad embeddings")
     if save_path:
         index.save(save_path)
         say(f"✓ FAISS index saved to {save_path}")

@@ -179,6 +179,27 @@ def test_build_faiss_index_device_pipeline(system, tmp_path):
     compare_topk(ids, d, rid, rd, 100, gap_tol=1e-6)
 
 
+def test_build_faiss_index_flat_streams_batches_into_reserved_buffers(system):
+    """index_type='Flat' (BASELINE config 1 asks for a flat index over all ads): every tower batch is added
+    straight into the pre-sized index, no intermediate embedding matrix; same answer as the oracle on the same
+    embeddings, ids = row numbers."""
+    import torch
+    from movie_recommender_demo_b200.training_pipeline import build_faiss_index
+    from oracle.compare import compare_topk
+    from oracle.flat import OracleFAISSIndex
+    from weights import make_inputs
+    _, _, acat = make_inputs(system["cfg"], 43, 9000)
+    index = build_faiss_index(system["model"], acat, "cuda", None, batch_size=1000, index_type='Flat')
+    assert index.index_type == 'Flat' and index.index.ntotal == 9000 and index.id_map == list(range(9000))
+    with torch.no_grad():
+        emb = system["model"].get_ad_embeddings(torch.from_numpy(acat).cuda()).cpu().numpy()
+    o = OracleFAISSIndex(256, 'Flat')
+    o.add(emb)
+    ids, d = index.search(emb[:16], k=100)
+    rid, rd = o.search(emb[:16], k=100, extra=32)
+    compare_topk(ids, d, rid, rd, 100, gap_tol=1e-6)
+
+
 def test_stage1_end_to_end_vs_reference_tower_golden(built_lib):
     """B200 towers + B200 Flat search vs tests/golden/stage1_cfg1.npz (embeddings from the reference's own
     towers, retrieval by the wrapper's order of operations).  The fp16-operand towers are within 1e-3 of the
