@@ -136,6 +136,11 @@ size_t b2r_index_search_workspace(const b2r_index* h, int q, int k, int nprobe);
  *            retry of the flagged queries.  Both may be NULL.
  *   tau_in   fp32 [q] device or NULL: caller-provided candidate thresholds
  *            (skips the sampling pass).
+ * Flagged queries: FLAT - pass tau_retry back as tau_in; IVF_FLAT with the fused list scan (chunks of >= 1024
+ * queries, taken only when `status` is given) - re-run those queries with set_param("ivf_fused", 0), whose
+ * threshold fallback is exact and in-kernel.  The Python wrappers do both.
+ * Tunables added in round 2 (b2r_index_set_param): pair_scan = 1 (default) | 0: FILTER scan of batches > 128 on
+ * CTA pairs (tcgen05 cta_group::2) or on single CTAs; ivf_fused = 1 (default) | 0.
  * Asynchronous on `stream`. */
 int b2r_index_search(b2r_index* h, int q, const float* queries, int normalize, int k,
                      int nprobe, float* D, int64_t* I, int32_t* status, float* tau_retry,

@@ -1452,7 +1452,8 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     // Below ~1k queries a list is scanned for a handful of pairs: the dump is small, and the fused path's two
     // extra launches (sample scan, segment gather) cost what the score round trip saves (measured at 10M x 256,
     // nlist 4096, nprobe 32: Q=64 0.53 vs 0.52 ms, Q=1024 a wash, Q=4096 see DESIGN.md 3.6).
-    const bool fused = pl.fused && !is_pq && qc >= 1024;
+    // (a caller that passes no status array cannot react to a flagged query: it gets the dump path, whose fallback is in-kernel)
+    const bool fused = pl.fused && !is_pq && qc >= 1024 && status != nullptr;
     if (is_pq) {
       // ADC scan: one CTA per (query, probed list) pair, LUT in shared memory (ivfpq.cu)
       if ((rc = pq_scan(h, qc, npairs, q32, coarse, np, pair_out, reinterpret_cast<float*>(ws + pl.off_qtab), scorebuf,
