@@ -265,16 +265,33 @@ int flat_search_chunk(b2r_index* h, const Plan& pl, int q, const float* queries,
     sel_cap_seg = pl.cap_seg;
   } else {
     ScanParams gp = sp;
-    gp.tile_stride = pl.s_stride;
-    gp.tile_count = pl.s_tiles;
     int mq, qg;
-    plan_scan(q, pl.s_tiles, h->num_sms, &mq, &qg, &gp.splits);
     gp.gmax = aux;
-    gp.gstride = (int)pl.gstride;
-    if ((rc = launch_scan(SCAN_GMAX, MQ, tmQ, h->tmX, gp, h->num_sms, stream))) return rc;
-    if ((rc = launch_kth_value(aux, q, pl.gstride, pl.gstride, pl.m_rank, tau, nullptr, nullptr, 0, nullptr, nullptr,
-                               0.f, stream)))
-      return rc;
+    const int s_pairs = pl.s_tiles / 2;
+    if (geo.pair && h->pair_gmax && s_pairs >= 1) {
+      // the sampling pass on CTA pairs too: s_tiles / 2 strided 256-row pair tiles, 8 group maxima each
+      const int tiles2 = (int)ceil_div(pl.tiles, 2);
+      gp.tile_count = s_pairs;
+      gp.tile_stride = tiles2 / s_pairs > 1 ? tiles2 / s_pairs : 1;
+      gp.gstride = s_pairs * 8;                       // <= pl.gstride: fits the planned buffer
+      gp.idesc = scan_idesc_pair(fp16);
+      plan_scan(q, s_pairs, h->num_sms / 2, &mq, &qg, &gp.splits);
+      const double G = (double)gp.gstride, frac = (double)s_pairs * 2 * kTileRows / (double)(h->ntotal > 0 ? h->ntotal : 1);
+      int m = (int)llround(G * (1.0 - exp(-(double)pl.c_target * (frac < 1.0 ? frac : 1.0) / G)));
+      if (m < 1) m = 1;
+      if ((rc = launch_scan_pair(tmQ, h->tmX, gp, h->num_sms, stream, 0, SCAN_GMAX))) return rc;
+      if ((rc = launch_kth_value(aux, q, gp.gstride, gp.gstride, m, tau, nullptr, nullptr, 0, nullptr, nullptr, 0.f, stream)))
+        return rc;
+    } else {
+      gp.tile_stride = pl.s_stride;
+      gp.tile_count = pl.s_tiles;
+      plan_scan(q, pl.s_tiles, h->num_sms, &mq, &qg, &gp.splits);
+      gp.gstride = (int)pl.gstride;
+      if ((rc = launch_scan(SCAN_GMAX, MQ, tmQ, h->tmX, gp, h->num_sms, stream))) return rc;
+      if ((rc = launch_kth_value(aux, q, pl.gstride, pl.gstride, pl.m_rank, tau, nullptr, nullptr, 0, nullptr, nullptr,
+                                 0.f, stream)))
+        return rc;
+    }
   }
   if (tau_in || !pl.dense) {
     const bool prof = h->profile && h->prof_used + 2 <= h->prof_ev.size();
@@ -566,6 +583,7 @@ int b2r_index_set_param(b2r_index* h, const char* name, double value) {
     h->epi_warps = (int)value;
   }
   else if (n == "pair_scan") h->pair_scan = value != 0;
+  else if (n == "pair_gmax") h->pair_gmax = value != 0;
   else if (n == "early_release") h->early_release = value != 0;
   else if (n == "walk") h->walk = value != 0;
   else if (n == "rescore") h->rescore = value != 0;
@@ -600,6 +618,7 @@ double b2r_index_get_param(const b2r_index* h, const char* name) {
   if (n == "cand_cap") return h->cand_cap;
   if (n == "epi_warps") return h->epi_warps;
   if (n == "pair_scan") return h->pair_scan;
+  if (n == "pair_gmax") return h->pair_gmax;
   if (n == "early_release") return h->early_release;
   if (n == "walk") return h->walk;
   if (n == "rescore") return h->rescore;

@@ -92,7 +92,7 @@ void plan_scan(int Q, int tile_count, int num_sms, int* MQ, int* QG, int* splits
 // FILTER scan on CTA pairs (scan_pair.cu, tcgen05 cta_group::2): p.QG = groups of 256 queries, p.tile_count =
 // 256-row pair tiles, p.nseg = 4 * p.splits, p.idesc = scan_idesc_pair()
 int launch_scan_pair(const CUtensorMap& tmQ, const CUtensorMap& tmX, const ScanParams& p, int num_sms,
-                     cudaStream_t stream, int walk);
+                     cudaStream_t stream, int walk, int mode = SCAN_FILTER);
 uint32_t scan_idesc_pair(int fp16);
 
 // --------------------------------------------------------- ingest / queries ---
@@ -167,6 +167,7 @@ struct b2r_index {
   int scan_fp16 = -1;       // current format of x16 (-1: nothing stored yet)
   double cand_factor_fp16 = 2.5;
   int walk = 1;                  // FILTER hit walk: 1 = only the passing 3-element sub-groups (2-5 % faster), 0 = all 8
+  int pair_gmax = 1;             // the threshold sampling pass of batches > 128 on CTA pairs as well (0: one-CTA GMAX scan)
   int early_release = 0;         // filter epilogue: release the TMEM buffer before the scores are examined (A/B: no gain)
   int pair_scan = 1;             // FILTER scan of batches > 128 on CTA pairs (tcgen05 cta_group::2, scan_pair.cu): 17-21 %
                                  // faster than the one-CTA kernel (1.58 -> 1.31 ms at Q=4096); 0 selects the one-CTA kernel

@@ -67,6 +67,28 @@ __device__ __forceinline__ void pair_filter_chunk(const uint32_t (&r)[32], float
   }
 }
 
+// maximum of one 32-row group (threshold sampling pass); rows past the corpus end do not count
+__device__ __forceinline__ float pair_group_max(const uint32_t (&r)[32], int rows_valid) {
+  float m = -INFINITY;
+  if (rows_valid == 32) {
+    float m0 = fmax3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
+    float m1 = fmax3(__uint_as_float(r[3]), __uint_as_float(r[4]), __uint_as_float(r[5]));
+#pragma unroll
+    for (int i = 6; i < 30; i += 4) {
+      m0 = fmax3(m0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+      m1 = fmax3(m1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+    }
+    m = fmax3(m0, m1, fmaxf(__uint_as_float(r[30]), __uint_as_float(r[31])));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < rows_valid) m = fmaxf(m, __uint_as_float(r[i]));
+  }
+  return m;
+}
+
+constexpr int kPairGmax = 2;   // MODE value: 0 / 1 = FILTER with the full / sub-group append walk, 2 = GMAX (sampling pass)
+
 template <int WALK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1)
 scan_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX,
@@ -212,10 +234,10 @@ scan_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int qbase = (qg * 2 + (int)rank) * kQBlock + quarter * 32;
       const int q = qbase + lane;
       const int segi = split * 4 + cq;
-      uint2* seg = p.cand + ((size_t)q * p.nseg + segi) * p.cap_seg;
+      uint2* seg = WALK == kPairGmax ? nullptr : p.cand + ((size_t)q * p.nseg + segi) * p.cap_seg;
       int cnt = 0;
       const bool warp_active = qbase < p.Q;
-      const float tau = p.tau[q];
+      const float tau = WALK == kPairGmax ? 0.f : p.tau[q];
       for (int j = j0; j < j1; ++j) {
         const uint32_t lead_tempty = mapa_u32(bar_tempty(tb), 0);
         mbar_wait(bar_tfull(tb), tph, 46);
@@ -234,15 +256,16 @@ scan_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(lead_tempty);
-          {
-            const int64_t rv = p.N - row_base;
-            const int rows_valid = rv >= 32 ? 32 : (rv < 0 ? 0 : (int)rv);
-            pair_filter_chunk<WALK>(r0, tau, row_base, rows_valid, seg, cnt, p.cap_seg);
-          }
-          {
-            const int64_t rv = p.N - (row_base + 32);
-            const int rows_valid = rv >= 32 ? 32 : (rv < 0 ? 0 : (int)rv);
-            pair_filter_chunk<WALK>(r1, tau, row_base + 32, rows_valid, seg, cnt, p.cap_seg);
+          const int64_t rv0 = p.N - row_base, rv1 = rv0 - 32;
+          const int valid0 = rv0 >= 32 ? 32 : (rv0 < 0 ? 0 : (int)rv0);
+          const int valid1 = rv1 >= 32 ? 32 : (rv1 < 0 ? 0 : (int)rv1);
+          if (WALK == kPairGmax) {
+            // sampling pass: the maxima of this warp's two 32-row groups of pair tile j -> gmax[q, j * 8 + cq * 2 ..]
+            float* dst = p.gmax + (size_t)q * p.gstride + j * 8 + cq * 2;      // 8-byte aligned (gstride % 8 == 0)
+            *reinterpret_cast<float2*>(dst) = make_float2(pair_group_max(r0, valid0), pair_group_max(r1, valid1));
+          } else {
+            pair_filter_chunk<WALK == kPairGmax ? 0 : WALK>(r0, tau, row_base, valid0, seg, cnt, p.cap_seg);
+            pair_filter_chunk<WALK == kPairGmax ? 0 : WALK>(r1, tau, row_base + 32, valid1, seg, cnt, p.cap_seg);
           }
         } else {
           tc_fence_before_sync();
@@ -251,7 +274,7 @@ scan_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         if (++tb == kPNB) { tb = 0; tph ^= 1; }
       }
-      if (warp_active) p.cand_count[(size_t)q * p.nseg + segi] = cnt;
+      if (WALK != kPairGmax && warp_active) p.cand_count[(size_t)q * p.nseg + segi] = cnt;
     }
   }
   __syncwarp();
@@ -265,25 +288,30 @@ scan_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 }  // namespace
 
-// p.QG = groups of 256 queries, p.tile_count = 256-row pair tiles, p.nseg = 4 * p.splits, p.idesc for M = N = 256
+// p.QG = groups of 256 queries, p.tile_count = 256-row pair tiles, p.idesc for M = N = 256.
+// mode SCAN_FILTER: p.nseg = 4 * p.splits; mode SCAN_GMAX: p.gmax [Qpad, gstride], gstride = 8 * tile_count.
 int launch_scan_pair(const CUtensorMap& tmQ, const CUtensorMap& tmX, const ScanParams& p, int num_sms,
-                     cudaStream_t stream, int walk) {
+                     cudaStream_t stream, int walk, int mode) {
   if (p.d % kKChunk != 0 || p.d < kKChunk || p.d > 256)
     return fail(B2R_EINVAL, "scan: d must be a multiple of 64 in [64,256]");
   if (p.tile_count <= 0 || p.Q <= 0) return B2R_OK;
-  if (p.nseg != 4 * p.splits) return fail(B2R_EINVAL, "pair scan: nseg must be 4 * splits");
+  if (mode == SCAN_FILTER && p.nseg != 4 * p.splits) return fail(B2R_EINVAL, "pair scan: nseg must be 4 * splits");
+  if (mode != SCAN_FILTER && mode != SCAN_GMAX) return fail(B2R_EINVAL, "pair scan: FILTER or GMAX");
+  if (mode == SCAN_GMAX && p.gstride < 8 * p.tile_count) return fail(B2R_EINVAL, "pair scan: gstride too small");
   const int64_t units = (int64_t)p.splits * p.QG;
   const int clusters = (int)(units < num_sms / 2 ? units : num_sms / 2);
-  static bool configured[2][64] = {};
+  const int w = mode == SCAN_GMAX ? kPairGmax : (walk ? 1 : 0);
+  static bool configured[3][64] = {};
   int dev = 0;
   B2R_CUDA(cudaGetDevice(&dev));
-  const int w = walk ? 1 : 0;
   if (!configured[w][dev & 63]) {
-    if (w) B2R_CUDA(cudaFuncSetAttribute(scan_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
+    if (w == 2) B2R_CUDA(cudaFuncSetAttribute(scan_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
+    else if (w == 1) B2R_CUDA(cudaFuncSetAttribute(scan_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
     else B2R_CUDA(cudaFuncSetAttribute(scan_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
     configured[w][dev & 63] = true;
   }
-  if (w) scan_pair_kernel<1><<<2 * clusters, kPThreads, kPSmem, stream>>>(tmQ, tmX, p);
+  if (w == 2) scan_pair_kernel<2><<<2 * clusters, kPThreads, kPSmem, stream>>>(tmQ, tmX, p);
+  else if (w == 1) scan_pair_kernel<1><<<2 * clusters, kPThreads, kPSmem, stream>>>(tmQ, tmX, p);
   else scan_pair_kernel<0><<<2 * clusters, kPThreads, kPSmem, stream>>>(tmQ, tmX, p);
   B2R_CHECK_LAUNCH("scan_pair_kernel");
   return B2R_OK;
