@@ -188,18 +188,32 @@ __global__ void pair_runs_kernel(const int64_t* __restrict__ coarse, int Q, int 
                                  const int64_t* __restrict__ list_off, int64_t smax,
                                  int64_t* __restrict__ pair_out, int* __restrict__ row_len,
                                  int* __restrict__ list_cnt) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  // one WARP per query, a lane per probe: the coarse -> list_off loads are two dependent round trips each, and a
+  // single thread walking nprobe = 32 of them serially was 8 us of a batch-1 search
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (q >= Q) return;
   int64_t cum = 0;
-  for (int j = 0; j < nprobe; ++j) {
-    const int64_t l = coarse[(size_t)q * nprobe + j];
-    pair_out[(size_t)q * nprobe + j] = (int64_t)q * smax + cum;
-    if (l >= 0) {
-      cum += (list_off[l + 1] - list_off[l] + 3) & ~(int64_t)3;   // runs start 16-byte aligned (float4 stores)
-      atomicAdd(list_cnt + l, 1);
+  for (int j0 = 0; j0 < nprobe; j0 += 32) {
+    const int j = j0 + lane;
+    int64_t len = 0;
+    if (j < nprobe) {
+      const int64_t l = coarse[(size_t)q * nprobe + j];
+      if (l >= 0) {
+        len = (list_off[l + 1] - list_off[l] + 3) & ~(int64_t)3;   // runs start 16-byte aligned (float4 stores)
+        atomicAdd(list_cnt + l, 1);
+      }
     }
+    int64_t incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (j < nprobe) pair_out[(size_t)q * nprobe + j] = (int64_t)q * smax + cum + (incl - len);
+    cum += __shfl_sync(0xffffffffu, incl, 31);
   }
-  row_len[q] = (int)cum;
+  if (lane == 0) row_len[q] = (int)cum;
 }
 
 // counting-sort scatter of pairs by list + gather of the pair's bf16 query row
@@ -1446,7 +1460,7 @@ int ivf_search(b2r_index* h, int q, const float* queries, int normalize, int k, 
     }
     B2R_CUDA(cudaMemsetAsync(listcnt, 0, (size_t)h->nlist * 4, stream));
     B2R_CUDA(cudaMemsetAsync(nunits, 0, 4, stream));
-    pair_runs_kernel<<<(unsigned)ceil_div(qc, 128), 128, 0, stream>>>(coarse, qc, np, h->list_off, pl.smax, pair_out,
+    pair_runs_kernel<<<(unsigned)ceil_div(qc, 4), 128, 0, stream>>>(coarse, qc, np, h->list_off, pl.smax, pair_out,
                                                                       row_len, listcnt);
     B2R_CHECK_LAUNCH("pair_runs_kernel");
     // Below ~1k queries a list is scanned for a handful of pairs: the dump is small, and the fused path's two

@@ -53,6 +53,16 @@ def _pipe_chunks(nq: int):
     one pass over the corpus), but the LAST chunk's device->host copy cannot hide behind anything, so the
     sizes shrink towards the tail: the last chunk is _PIPE_CHUNK queries and each earlier one at most 4x
     its successor (a chunk's result copy takes ~1/5 of the same chunk's search, so it hides under the next)."""
+    import os
+    forced = os.environ.get("B2R_PIPE_SIZES")            # measurement hook: "3584,512" = explicit chunk sizes
+    if forced:
+        sizes = [int(v) for v in forced.split(",")]
+        if sum(sizes) == nq and all(v > 0 for v in sizes):
+            out, lo = [], 0
+            for v in sizes:
+                out.append((lo, lo + v))
+                lo += v
+            return out
     sizes = [min(nq, _PIPE_CHUNK)]
     left = nq - sizes[0]
     while left > 0:

@@ -33,3 +33,9 @@ def d2h2():
 print("d2h D+I (reused pinned)", t(d2h2))
 print("index.index.search(np) ", t(lambda: idx.index.search(qn, 500, normalize=True)))
 print("FAISSIndex.search(np)  ", t(lambda: idx.search(qn, k=500)))
+
+import os
+for sizes in sys.argv[2:]:                       # explicit pipeline chunk sizes, e.g. 3584,512
+    os.environ["B2R_PIPE_SIZES"] = sizes
+    print(f"FAISSIndex.search(np) chunks {sizes:16s}", t(lambda: idx.search(qn, k=500)), flush=True)
+os.environ.pop("B2R_PIPE_SIZES", None)
