@@ -257,6 +257,22 @@ double b2r_tower_get_param(const b2r_tower* t, const char* name);
 int b2r_tower_forward(b2r_tower* t, const int64_t* cat, const float* num, int64_t B, float* out,
                       int32_t* err_flag, void* workspace, size_t ws_bytes, void* stream);
 
+/* Peer-memory exchange (csrc/peer.cu): the small-batch alternative to the NCCL all-gather of the packed lists.
+ * Every rank creates a context (one cudaMalloc'd buffer: control block + receive area of `cap_bytes`), the 64-byte
+ * cudaIpcMemHandle blobs are exchanged by the host (e.g. one torch.distributed all_gather), b2r_peer_connect maps
+ * the peers' buffers.  b2r_peer_allgather(send, bytes) then copies `send` into slot [rank] of EVERY rank's receive
+ * area with P2P stores over NVLink and waits (on the stream, bounded) until all P slots of the local area are
+ * filled: *recv + r * bytes = rank r's data - the layout b2r_topk_merge_packed expects with q_stride = q.  After the
+ * consumer kernel, b2r_peer_ack releases the area for the peers' next push.  Collective calls: same order and
+ * same `bytes` on every rank.  Epochs live in device memory: the sequence can be captured in a CUDA graph. */
+typedef struct b2r_peer b2r_peer;
+int b2r_peer_create(b2r_peer** out, int rank, int world, size_t cap_bytes, int device);
+int b2r_peer_destroy(b2r_peer* c);
+int b2r_peer_handle(b2r_peer* c, void* handle64);
+int b2r_peer_connect(b2r_peer* c, const void* handles);
+int b2r_peer_allgather(b2r_peer* c, const void* send, size_t bytes, void** recv, void* stream);
+int b2r_peer_ack(b2r_peer* c, void* stream);
+
 /* ------------------------------------------------------ Stage-2 ranker -- */
 /* TransformerRanker.forward (transformer_ranker.py:332-380) in eval mode, as called with
  * stage1_k = 500 candidate rows per user at inference.py:250-255 and faiss_retrieval.py:351-355.

@@ -111,6 +111,12 @@ def load():
         "b2r_topk_merge": (i32, [i32, i32, i32, vp, vp, vp, vp, i32, vp]),
         "b2r_topk_pack": (i32, [i32, i32, i32, vp, vp, vp, i64, vp, i32, vp]),
         "b2r_topk_merge_packed": (i32, [i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]),
+        "b2r_peer_create": (i32, [C.POINTER(vp), i32, i32, sz, i32]),
+        "b2r_peer_destroy": (i32, [vp]),
+        "b2r_peer_handle": (i32, [vp, vp]),
+        "b2r_peer_connect": (i32, [vp, vp]),
+        "b2r_peer_allgather": (i32, [vp, vp, sz, C.POINTER(vp), vp]),
+        "b2r_peer_ack": (i32, [vp, vp]),
         "b2r_gather_concat": (i32, [vp, vp, i32, i32, vp, i64, vp, i64, vp, vp]),
         "b2r_tower_create": (i32, [C.POINTER(vp), C.POINTER(TowerWeights), i32]),
         "b2r_tower_destroy": (i32, [vp]),

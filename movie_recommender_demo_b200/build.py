@@ -18,7 +18,7 @@ CSRC = PKG_DIR / "csrc"
 OBJ_DIR = PKG_DIR / "_build"
 LIB_PATH = PKG_DIR / "libb2retr.so"
 
-SOURCES = ["scan_tc.cu", "scan_pair.cu", "ingest.cu", "select.cu", "index.cu", "tower.cu", "tower_mlp.cu", "tower_fused.cu", "ranker.cu", "ivf.cu", "ivfpq.cu", "persist.cu"]
+SOURCES = ["scan_tc.cu", "scan_pair.cu", "ingest.cu", "select.cu", "index.cu", "tower.cu", "tower_mlp.cu", "tower_fused.cu", "ranker.cu", "ivf.cu", "ivfpq.cu", "persist.cu", "peer.cu"]
 
 NVCC_FLAGS = [
     "-O3",

@@ -127,11 +127,78 @@ class ShardedFlatIndex:
                                              self._largest, int(torch.cuda.current_stream(Dl.device).cuda_stream)))
 
     def _merge(self, P, q, q_stride, k, packed, D_out, I_out, st_out):
+        """`packed`: a tensor, or the raw device pointer (int) of the peer exchange's receive area"""
         torch = self._torch
-        _lib.check(_lib.load().b2r_topk_merge_packed(P, q, q_stride, k, packed.data_ptr(),
-                                                     self._shard_bases(packed.device).data_ptr(), D_out.data_ptr(),
+        dev = D_out.device
+        ptr = packed if isinstance(packed, int) else packed.data_ptr()
+        _lib.check(_lib.load().b2r_topk_merge_packed(P, q, q_stride, k, ptr,
+                                                     self._shard_bases(dev).data_ptr(), D_out.data_ptr(),
                                                      I_out.data_ptr(), st_out.data_ptr(), self._largest,
-                                                     int(torch.cuda.current_stream(packed.device).cuda_stream)))
+                                                     int(torch.cuda.current_stream(dev).cuda_stream)))
+
+    # ---- peer-memory exchange (csrc/peer.cu): P2P stores over NVLink instead of the NCCL all-gather, for the
+    #      latency-bound "gather" batches.  Opt-in: B2R_PEER_EXCHANGE=1 or `index.peer_exchange = True`.
+    peer_exchange = None          # None: follow the environment variable
+
+    def _peer_enabled(self) -> bool:
+        want = self.peer_exchange if self.peer_exchange is not None else os.environ.get("B2R_PEER_EXCHANGE") == "1"
+        return bool(want) and self.world > 1 and self.local.device.type == "cuda" and self.group is None
+
+    def _peer_ctx(self, need_bytes: int):
+        """The (lazily created) exchange context of this index: one IPC-shared buffer per rank.  Collective."""
+        import ctypes as C
+        import torch.distributed as dist
+        ctx = getattr(self, "_peer", None)
+        if ctx is not None and ctx["cap"] >= need_bytes:
+            return ctx
+        torch = self._torch
+        lib = _lib.load()
+        dev = self.local.device
+        if ctx is not None:
+            torch.cuda.synchronize(dev)
+            dist.barrier()                       # nobody may still be pushing into the buffer that goes away
+            lib.b2r_peer_destroy(ctx["h"])
+            self._graphs = {}
+        cap = max(need_bytes, 4 << 20)
+        h = C.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(lib.b2r_peer_create(C.byref(h), self.rank, self.world, cap, dev.index))
+            blob = (C.c_ubyte * 64)()
+            _lib.check(lib.b2r_peer_handle(h, blob))
+            mine = torch.tensor(list(blob), dtype=torch.uint8, device=dev)
+            allh = torch.empty((self.world, 64), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, mine)
+            raw = bytes(allh.cpu().numpy().tobytes())
+            _lib.check(lib.b2r_peer_connect(h, raw))
+        dist.barrier()                           # every rank has mapped every buffer before the first push
+        self._peer = {"h": h, "cap": cap}
+        return self._peer
+
+    def _peer_allgather(self, send, nbytes: int) -> int:
+        import ctypes as C
+        torch = self._torch
+        ctx = self._peer
+        recv = C.c_void_p()
+        with torch.cuda.device(send.device):
+            _lib.check(_lib.load().b2r_peer_allgather(ctx["h"], send.data_ptr(), nbytes, C.byref(recv),
+                                                      int(torch.cuda.current_stream(send.device).cuda_stream)))
+        return int(recv.value)
+
+    def _peer_ack(self, dev) -> None:
+        torch = self._torch
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().b2r_peer_ack(self._peer["h"], int(torch.cuda.current_stream(dev).cuda_stream)))
+
+    def close(self) -> None:
+        """Release the captured graphs and the peer-exchange buffers (collective when the latter exist)."""
+        self.release_graphs()
+        ctx = getattr(self, "_peer", None)
+        if ctx is not None:
+            import torch.distributed as dist
+            self._torch.cuda.synchronize(self.local.device)
+            dist.barrier()
+            _lib.load().b2r_peer_destroy(ctx["h"])
+            self._peer = None
 
     def _exchange(self, Dl, Il, st, k: int, bufs=None):
         """Packed exchange + merge of this rank's local result.  Returns (D, I, status) [Q,k] / [Q] tensors,
@@ -153,6 +220,23 @@ class ShardedFlatIndex:
             D_out = buf("D", (Q, k), torch.float32)
             I_out = buf("I", (Q, k), torch.int64)
             st_out = buf("st", (Q,), torch.int32)
+            nbytes = (Q * W * 4 + 15) // 16 * 16
+            if self._peer_enabled():
+                # packed list -> slot [rank] of every rank's receive area by P2P stores; rank r's block starts at
+                # recv + r * nbytes, so the merge's block stride is nbytes / 4 words = (nbytes / 4 / W) rows only when
+                # Q * W * 4 is a multiple of 16: pad the row count of the packed buffer instead
+                rows = Q
+                while (rows * W * 4) % 16:
+                    rows += 1
+                nbytes = rows * W * 4
+                if not torch.cuda.is_current_stream_capturing():
+                    self._peer_ctx(P * nbytes)
+                send = buf("send", (rows, W), torch.int32)
+                self._pack(Q, rows, k, Dl, Il, st, send)
+                recv_ptr = self._peer_allgather(send, nbytes)
+                self._merge(P, Q, rows, k, recv_ptr, D_out, I_out, st_out)
+                self._peer_ack(dev)
+                return D_out, I_out, st_out
             send = buf("send", (Q, W), torch.int32)
             recv = buf("recv", (P, Q, W), torch.int32)
             self._pack(Q, Q, k, Dl, Il, st, send)

@@ -75,6 +75,23 @@ os.environ["B2R_NO_GRAPHS"] = "1"
 Dm, Im, st = sh.search_device(q, K)             # the same exchange launched eagerly
 report(f"flat Q={Q} [{exchange_mode(Q, world)} exchange, eager]", Dm, Im, st, q)
 del os.environ["B2R_NO_GRAPHS"]
+# 1b) the same small batch through the PEER-MEMORY exchange (csrc/peer.cu: P2P stores over NVLink + flags instead
+#     of the NCCL all-gather), captured in a graph, replayed, and eager; a second batch size re-sizes nothing
+sh.peer_exchange = True
+sh._graphs = {}
+for tag in ("first (capture)", "replay", "replay 2"):
+    Dm, Im, st = sh.search_device(q, K)
+    report(f"flat Q={Q} [peer-memory exchange, graph {tag}]", Dm, Im, st, q)
+os.environ["B2R_NO_GRAPHS"] = "1"
+for rep in range(3):
+    Dm, Im, st = sh.search_device(q, K)
+report(f"flat Q={Q} [peer-memory exchange, eager x3]", Dm, Im, st, q)
+q7 = q[:7].contiguous()
+Dm, Im, st = sh.search_device(q7, K)
+report("flat Q=7 [peer-memory exchange, eager, padded rows]", Dm, Im, st, q7)
+del os.environ["B2R_NO_GRAPHS"]
+sh.peer_exchange = False
+sh._graphs = {}
 # 2) large batch: all-to-all by query slice + merge of one slice per rank + all-gather of the merged slices
 Dm, Im, st = sh.search_device(qb, K)
 report(f"flat Q={QB} [{exchange_mode(QB, world)} exchange]", Dm, Im, st, qb)
