@@ -137,12 +137,16 @@ class ShardedFlatIndex:
                                                      int(torch.cuda.current_stream(dev).cuda_stream)))
 
     # ---- peer-memory exchange (csrc/peer.cu): P2P stores over NVLink instead of the NCCL all-gather, for the
-    #      latency-bound "gather" batches.  Opt-in: B2R_PEER_EXCHANGE=1 or `index.peer_exchange = True`.
-    peer_exchange = None          # None: follow the environment variable
+    #      latency-bound "gather" batches.  On by default for CUDA ranks of the default process group;
+    #      B2R_PEER_EXCHANGE=0 or `index.peer_exchange = False` selects the NCCL all-gather.  If any rank fails to
+    #      map a peer's buffer (no CUDA IPC in this container, no P2P path), ALL ranks fall back to NCCL together.
+    peer_exchange = None          # None: follow the environment variable (default on)
 
-    def _peer_enabled(self) -> bool:
-        want = self.peer_exchange if self.peer_exchange is not None else os.environ.get("B2R_PEER_EXCHANGE") == "1"
-        return bool(want) and self.world > 1 and self.local.device.type == "cuda" and self.group is None
+    def _peer_enabled(self, dev) -> bool:
+        if getattr(self, "_peer_broken", False) or dev.type != "cuda":
+            return False
+        want = self.peer_exchange if self.peer_exchange is not None else os.environ.get("B2R_PEER_EXCHANGE", "1") != "0"
+        return bool(want) and self.world > 1 and getattr(self, "group", None) is None
 
     def _peer_ctx(self, need_bytes: int):
         """The (lazily created) exchange context of this index: one IPC-shared buffer per rank.  Collective."""
@@ -161,16 +165,26 @@ class ShardedFlatIndex:
             self._graphs = {}
         cap = max(need_bytes, 4 << 20)
         h = C.c_void_p()
+        ok, why = 1, ""
         with torch.cuda.device(dev):
-            _lib.check(lib.b2r_peer_create(C.byref(h), self.rank, self.world, cap, dev.index))
             blob = (C.c_ubyte * 64)()
-            _lib.check(lib.b2r_peer_handle(h, blob))
+            if lib.b2r_peer_create(C.byref(h), self.rank, self.world, cap, dev.index) != 0 or \
+                    lib.b2r_peer_handle(h, blob) != 0:
+                ok, why = 0, (lib.b2r_last_error() or b"").decode()
             mine = torch.tensor(list(blob), dtype=torch.uint8, device=dev)
             allh = torch.empty((self.world, 64), dtype=torch.uint8, device=dev)
             dist.all_gather_into_tensor(allh, mine)
-            raw = bytes(allh.cpu().numpy().tobytes())
-            _lib.check(lib.b2r_peer_connect(h, raw))
-        dist.barrier()                           # every rank has mapped every buffer before the first push
+            if ok and lib.b2r_peer_connect(h, bytes(allh.cpu().numpy().tobytes())) != 0:
+                ok, why = 0, (lib.b2r_last_error() or b"").decode()
+            agree = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN)     # also: every rank has mapped every buffer before the first push
+        if int(agree.item()) == 0:
+            if h:
+                lib.b2r_peer_destroy(h)
+            self._peer, self._peer_broken = None, True
+            warnings.warn("sharded search: peer-memory exchange unavailable on some rank"
+                          + (f" ({why})" if why else "") + "; using the NCCL all-gather")
+            return None
         self._peer = {"h": h, "cap": cap}
         return self._peer
 
@@ -221,7 +235,7 @@ class ShardedFlatIndex:
             I_out = buf("I", (Q, k), torch.int64)
             st_out = buf("st", (Q,), torch.int32)
             nbytes = (Q * W * 4 + 15) // 16 * 16
-            if self._peer_enabled():
+            if self._peer_enabled(dev):
                 # packed list -> slot [rank] of every rank's receive area by P2P stores; rank r's block starts at
                 # recv + r * nbytes, so the merge's block stride is nbytes / 4 words = (nbytes / 4 / W) rows only when
                 # Q * W * 4 is a multiple of 16: pad the row count of the packed buffer instead
@@ -229,14 +243,16 @@ class ShardedFlatIndex:
                 while (rows * W * 4) % 16:
                     rows += 1
                 nbytes = rows * W * 4
+                ctx = getattr(self, "_peer", None)
                 if not torch.cuda.is_current_stream_capturing():
-                    self._peer_ctx(P * nbytes)
-                send = buf("send", (rows, W), torch.int32)
-                self._pack(Q, rows, k, Dl, Il, st, send)
-                recv_ptr = self._peer_allgather(send, nbytes)
-                self._merge(P, Q, rows, k, recv_ptr, D_out, I_out, st_out)
-                self._peer_ack(dev)
-                return D_out, I_out, st_out
+                    ctx = self._peer_ctx(P * nbytes)
+                if ctx is not None:
+                    send = buf("send", (rows, W), torch.int32)
+                    self._pack(Q, rows, k, Dl, Il, st, send)
+                    recv_ptr = self._peer_allgather(send, nbytes)
+                    self._merge(P, Q, rows, k, recv_ptr, D_out, I_out, st_out)
+                    self._peer_ack(dev)
+                    return D_out, I_out, st_out
             send = buf("send", (Q, W), torch.int32)
             recv = buf("recv", (P, Q, W), torch.int32)
             self._pack(Q, Q, k, Dl, Il, st, send)

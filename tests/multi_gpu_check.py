@@ -66,6 +66,8 @@ def report(tag, Dm, Im, st, queries):
 from movie_recommender_demo_b200.sharded import exchange_mode  # noqa: E402
 
 # 1) small batch: packed all-gather exchange, replayed as a CUDA graph (local search + pack + NCCL + merge)
+sh.peer_exchange = False                         # first the NCCL all-gather form of the small-batch exchange
+sh._graphs = {}
 Dm, Im, st = sh.search_device(q, K)
 report(f"flat Q={Q} [{exchange_mode(Q, world)} exchange, graph replay={bool(sh._graphs and any(sh._graphs.values()))}]",
        Dm, Im, st, q)
