@@ -7,6 +7,7 @@ symbol-export test); every compute entry point needs a B200.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import re
 from pathlib import Path
 
@@ -74,11 +75,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    lib_path = Path(os.environ["B2R_LIB_PATH"]) if os.environ.get("B2R_LIB_PATH") else LIB_PATH   # A/B builds (measurement only)
+    if not lib_path.exists():
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `python -m movie_recommender_demo_b200.build` "
+            f"{lib_path} is missing: build it with `python -m movie_recommender_demo_b200.build` "
             "(there is no CPU fallback)")
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(lib_path))
     vp, i64, i32, sz, dbl = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_double
     sig = {
         "b2r_version": (i32, []),

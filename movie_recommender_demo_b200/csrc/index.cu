@@ -591,6 +591,10 @@ int b2r_index_set_param(b2r_index* h, const char* name, double value) {
   else if (n == "dense_budget") h->dense_budget = (int64_t)value;
   else if (n == "ivf_sample") h->ivf_sample = (int)value;
   else if (n == "ivf_fused") h->ivf_fused = value != 0;
+  else if (n == "ivf_sample_rows") {
+    if (value < 4 || value > 128 || ((int)value & 3)) return fail(B2R_EINVAL, "ivf_sample_rows must be a multiple of 4 in [4,128]");
+    h->ivf_sample_rows = (int)value;
+  }
   else if (n == "ivf_debug") h->ivf_debug = (int)value;
   else if (n == "pq_scan_path") h->pq_scan_path = (int)value;
   else if (n == "profile") {
@@ -626,6 +630,7 @@ double b2r_index_get_param(const b2r_index* h, const char* name) {
   if (n == "dense_budget") return (double)h->dense_budget;
   if (n == "ivf_sample") return h->ivf_sample;
   if (n == "ivf_fused") return h->ivf_fused;
+  if (n == "ivf_sample_rows") return h->ivf_sample_rows;
   if (n == "num_sms") return h->num_sms;
   if (n == "scan_ms_avg" || n == "scan_launches") {
     // mean device time of the timed filter-scan launches (synchronises on their events)

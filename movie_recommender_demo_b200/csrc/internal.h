@@ -178,6 +178,7 @@ struct b2r_index {
   int force_path = 0;  // 0 auto, 1 dense, 2 filter (tests)
   int pq_scan_path = 0;  // 0 auto (query-major when pq_m allows), 1 force the (query, list)-pair kernel (tests)
   int ivf_debug = 0;   // profiling experiments (never set in production)
+  int ivf_sample_rows = 128;  // fused IVF path: rows of every probed list the sample pass scores (<= 128 = one tile)
   int ivf_fused = 1;   // IVF-Flat: threshold filter fused into the list scan (sample pass + filter scan); 0 = dump all pair scores
   int ivf_sample = 1;  // IVF candidate threshold from a score sample (0: always the exact radix passes)
   int64_t dense_budget = (int64_t)1 << 30;  // bytes of dumped scores per query chunk

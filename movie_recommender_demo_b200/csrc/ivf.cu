@@ -1336,7 +1336,7 @@ IvfPlan make_ivf_plan(const b2r_index* h, int q, int k, int nprobe) {
   // fused path: the filter scan appends candidates to private segments inside the pair runs (8 bytes per slot
   // instead of 4 per dumped score, touched only where a candidate lands).  Needs the sample of every probed list
   // to fit the threshold kernel's sort buffer and the query's segment list to fit the gather kernel's.
-  pl.sample_rows = std::max(4, std::min(128, (kIvfTauMaxKeys / nprobe) & ~3));
+  pl.sample_rows = std::max(4, std::min(h->ivf_sample_rows, (kIvfTauMaxKeys / nprobe) & ~3));
   int64_t worst_sub = 0;
   for (int i = 0; i < nprobe && i < (int)sz.size(); ++i)
     worst_sub += 2 * ceil_div(ceil_div(sz[i] > 0 ? sz[i] : 1, kTileRows), kUnitTilesSmallQ);

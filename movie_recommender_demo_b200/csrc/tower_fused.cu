@@ -42,7 +42,13 @@ namespace {
 constexpr int kFtThreads = 640;
 constexpr int kFtEpiWarp0 = 4, kFtEpiWarps = 8;
 constexpr int kFtGatherWarp0 = 12, kFtGatherWarps = 8;
-constexpr int kNA = 3, kNW = 3;               // ring depths (16 KB slots)
+#ifndef B2R_FT_NA
+#define B2R_FT_NA 3
+#endif
+#ifndef B2R_FT_NW
+#define B2R_FT_NW 3
+#endif
+constexpr int kNA = B2R_FT_NA, kNW = B2R_FT_NW;   // ring depths (16 KB slots); -D overrides are for A/B builds only
 constexpr int kHBytes = 131072;
 constexpr int kSlot = 16384;
 constexpr int kMaxKC = 8;                     // 64-column chunks of H1 (N1p <= 512)

@@ -31,6 +31,7 @@ import os
 fused = int(os.environ.get('B2R_IVF_FUSED', '1'))
 if kind == 'IVF':
     idx.index.set_param('ivf_fused', fused)
+    idx.index.set_param('ivf_sample_rows', int(os.environ.get('B2R_IVF_SAMPLE_ROWS', '128')))
 q = torch.nn.functional.normalize(centres[torch.randint(0, nlist, (Q,), generator=g, device=dev)] + 0.35 * torch.randn((Q, 256), generator=g, device=dev), dim=1)
 for _ in range(2):
     idx.index.search_device(q, 500, normalize=True)
@@ -39,7 +40,10 @@ t0 = time.perf_counter()
 for _ in range(steps):
     idx.index.search_device(q, 500, normalize=True)
 torch.cuda.synchronize()
-print(f"fused={fused} debug={debug} {kind} N={N} nlist={nlist} Q={Q} sample={sample}: {(time.perf_counter() - t0) / steps * 1e3:.3f} ms/step")
+ms_step = (time.perf_counter() - t0) / steps * 1e3        # BEFORE anything else touches the device
+_, _, _st, _ = idx.index.search_device(q, 500, normalize=True)
+print(f"flagged={int((_st != 0).sum())} sample_rows={os.environ.get('B2R_IVF_SAMPLE_ROWS', '128')}", end=" ")
+print(f"fused={fused} debug={debug} {kind} N={N} nlist={nlist} Q={Q} sample={sample}: {ms_step:.3f} ms/step")
 import os
 if os.environ.get("PROF_TABLE"):
     from torch.profiler import profile, ProfilerActivity
