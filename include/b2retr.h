@@ -230,6 +230,24 @@ typedef struct b2r_tower_weights {
 
 /* Replaces UserTower/AdTower construction + load_state_dict + eval(). */
 int b2r_tower_create(b2r_tower** out, const b2r_tower_weights* w, int device);
+
+/* The same for `hidden_dims` of ANY length (two_tower_model.py:83-95 / :152-164 build one
+ * Linear+BatchNorm+ReLU+Dropout block per entry; train.py:350 exposes --hidden_dims with nargs='+').
+ * num_layers = len(hidden_dims) + 1 Linear layers, 1..16; widths[l] = fan-out of layer l (the last one is
+ * output_dim, <= 256); w[l] = BN-folded fp32 [widths[l], fan_in_l] row-major, b[l] = [widths[l]], all HOST.
+ * b2r_tower_create is this call with num_layers = 3.  Towers with two hidden layers whose widths fit
+ * (<= 512 / 256 / 256) take the fused kernel; every other shape runs gather + one tcgen05 GEMM launch per
+ * layer (hidden activations 16-bit in the caller's workspace, see b2r_tower_workspace). */
+typedef struct b2r_tower_layers {
+  int num_fields, emb_dim, num_numerical;
+  int num_layers;
+  const int64_t* cards;       /* [F] host */
+  const float* const* tables; /* [F] DEVICE pointers */
+  const int* widths;          /* [num_layers] host */
+  const float* const* w;      /* [num_layers] host pointers */
+  const float* const* b;      /* [num_layers] host pointers */
+} b2r_tower_layers;
+int b2r_tower_create_layers(b2r_tower** out, const b2r_tower_layers* w, int device);
 int b2r_tower_destroy(b2r_tower* t);
 /* Workspace bytes b2r_tower_forward needs for a batch of B (0 when the fused kernel serves this tower:
  * it keeps every intermediate activation on the SM). */
@@ -238,7 +256,8 @@ size_t b2r_tower_workspace(const b2r_tower* t, int64_t B);
 /* Tunables: operand_dtype = 0 fp16 (default: 8x smaller rounding error than bf16, same tensor rate) | 1 bf16
  * (fp32 range; chosen automatically at create time when a BN-folded weight exceeds the fp16 range, and by the
  * caller when a forward reports B2R_TOWER_SATURATED); force_path = 0 auto | 1 layer-by-layer kernels (gather +
- * 3 GEMM launches, any widths) | 2 fused kernel (hidden widths <= 512 / 256, out_dim <= 256 and % 4 == 0).
+ * one GEMM launch per layer, any widths, any depth) | 2 fused kernel (two hidden layers of widths <= 512 / 256,
+ * out_dim <= 256 and % 4 == 0).
  * get_param also answers "fused" (1 when the next forward takes the fused kernel). */
 int b2r_tower_set_param(b2r_tower* t, const char* name, double value);
 double b2r_tower_get_param(const b2r_tower* t, const char* name);

@@ -43,6 +43,19 @@ class TowerWeights(C.Structure):
     ]
 
 
+class TowerLayers(C.Structure):
+    """struct b2r_tower_layers (include/b2retr.h): a tower with any number of hidden layers."""
+    _fields_ = [
+        ("num_fields", C.c_int), ("emb_dim", C.c_int), ("num_numerical", C.c_int),
+        ("num_layers", C.c_int),
+        ("cards", C.POINTER(C.c_int64)),
+        ("tables", C.POINTER(C.c_void_p)),
+        ("widths", C.POINTER(C.c_int)),
+        ("w", C.POINTER(C.c_void_p)),
+        ("b", C.POINTER(C.c_void_p)),
+    ]
+
+
 class RankerWeights(C.Structure):
     """struct b2r_ranker_weights (include/b2retr.h)."""
     _fields_ = [
@@ -121,6 +134,7 @@ def load():
         "b2r_peer_ack": (i32, [vp, vp]),
         "b2r_gather_concat": (i32, [vp, vp, i32, i32, vp, i64, vp, i64, vp, vp]),
         "b2r_tower_create": (i32, [C.POINTER(vp), C.POINTER(TowerWeights), i32]),
+        "b2r_tower_create_layers": (i32, [C.POINTER(vp), C.POINTER(TowerLayers), i32]),
         "b2r_tower_destroy": (i32, [vp]),
         "b2r_tower_workspace": (sz, [vp, i64]),
         "b2r_tower_set_param": (i32, [vp, C.c_char_p, dbl]),

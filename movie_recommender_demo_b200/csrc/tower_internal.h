@@ -5,12 +5,16 @@
 
 #include "internal.h"
 
+// hidden_dims of any length (two_tower_model.py:83-95 loops over the list): up to 15 hidden layers + the output layer
+constexpr int kTowerMaxLayers = 16;
+
 struct b2r_tower {
   int device = 0, num_sms = 148;
   int F = 0, E = 0, nnum = 0;
   int K1 = 0, K1p = 0;           // layer-1 fan-in and its 64-padding
-  int n[3] = {0, 0, 0};          // true fan-outs
-  int np[3] = {0, 0, 0};         // padded to a multiple of 128
+  int L = 3;                     // Linear layers (hidden layers + the output layer); the fused kernel serves L == 3
+  int n[kTowerMaxLayers] = {};   // true fan-outs
+  int np[kTowerMaxLayers] = {};  // padded to a multiple of 128
   // operand format of activations and weights: 0 = IEEE fp16 (default: 8x smaller rounding error),
   // 1 = bf16 (fp32 range; chosen when a folded weight, an input or a hidden activation would exceed
   // the fp16 range).  Both weight copies are kept so the switch costs nothing at run time.
@@ -19,15 +23,15 @@ struct b2r_tower {
   int pair = 1;                  // fused kernel on CTA pairs (tcgen05 cta_group::2, 256-column weight tiles) when every padded
                                  // width is a multiple of 256: 0.148 -> 0.139 ms at B = 65536; set_param("pair", 0) = one CTA per tile
   uintptr_t trace_ptr = 0;       // debug: device buffer for the fused kernel's phase timeline (tests/prof_tower.py)
-  __half* w[3] = {nullptr, nullptr, nullptr};          // [np[l], Kp[l]] fp16, zero padded
-  __nv_bfloat16* wb[3] = {nullptr, nullptr, nullptr};  // the same weights in bf16
-  float* b[3] = {nullptr, nullptr, nullptr};           // [np[l]]
+  __half* w[kTowerMaxLayers] = {};          // [np[l], Kp[l]] fp16, zero padded
+  __nv_bfloat16* wb[kTowerMaxLayers] = {};  // the same weights in bf16
+  float* b[kTowerMaxLayers] = {};           // [np[l]]
   float bias_host[1024];         // b1 | b2 | b3 (padded), passed to the fused kernel by value
   const float** tables = nullptr;  // device array [F]
   int64_t* cards = nullptr;        // device array [F]
-  CUtensorMap tmW[3], tmWb[3];     // layer-by-layer path: box rows 256 / 128
+  CUtensorMap tmW[kTowerMaxLayers], tmWb[kTowerMaxLayers];   // layer-by-layer path: box rows 256 / 128
   CUtensorMap tmWf[3], tmWfb[3];   // fused path: box {64, 128}
-  bool fused_ok = false;           // shape fits the fused kernel (widths <= 512/256/256)
+  bool fused_ok = false;           // shape fits the fused kernel (two hidden layers, widths <= 512/256/256)
 };
 
 namespace b2r {

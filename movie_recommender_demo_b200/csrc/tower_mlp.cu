@@ -339,11 +339,13 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (grow < p.M) {
               const int col = n0 + c * 32 + rd_j * 4;
               float* o = obase + grow * p.ldo + c * 32 + rd_j * 4;
-              if (col + 4 <= p.n_store) *reinterpret_cast<uint4*>(o) = v;
+              // 16-byte stores need rows that start 16-byte aligned (ldo % 4 == 0, e.g. not output_dim = 50)
+              if (col + 4 <= p.n_store && (p.ldo & 3) == 0) *reinterpret_cast<uint4*>(o) = v;
               else {
                 if (col < p.n_store) o[0] = __uint_as_float(v.x);
                 if (col + 1 < p.n_store) o[1] = __uint_as_float(v.y);
                 if (col + 2 < p.n_store) o[2] = __uint_as_float(v.z);
+                if (col + 3 < p.n_store) o[3] = __uint_as_float(v.w);
               }
             }
           }
@@ -469,7 +471,7 @@ extern "C" {
 
 int b2r_tower_destroy(b2r_tower* t) {
   if (!t) return B2R_OK;
-  for (int l = 0; l < 3; ++l) {
+  for (int l = 0; l < kTowerMaxLayers; ++l) {
     cudaFree(t->w[l]);
     cudaFree(t->wb[l]);
     cudaFree(t->b[l]);
@@ -480,12 +482,19 @@ int b2r_tower_destroy(b2r_tower* t) {
   return B2R_OK;
 }
 
-int b2r_tower_create(b2r_tower** out, const b2r_tower_weights* w, int device) {
+int b2r_tower_create_layers(b2r_tower** out, const b2r_tower_layers* w, int device) {
   if (!out || !w) return fail(B2R_EINVAL, "tower_create: NULL argument");
   *out = nullptr;
   if (w->num_fields < 1 || w->emb_dim < 4 || w->emb_dim % 4 != 0 || w->num_numerical < 0)
     return fail(B2R_EINVAL, "tower_create: bad embedding configuration");
-  if (w->hidden1 < 1 || w->hidden2 < 1 || w->out_dim < 1 || w->out_dim > 256)
+  const int L = w->num_layers;
+  if (L < 1 || L > kTowerMaxLayers)
+    return fail(B2R_EUNSUPPORTED, "tower_create: 1 to " + std::to_string(kTowerMaxLayers) +
+                                      " Linear layers (hidden layers + output layer) are supported");
+  if (!w->widths || !w->w || !w->b) return fail(B2R_EINVAL, "tower_create: NULL layer arrays");
+  for (int l = 0; l < L; ++l)
+    if (w->widths[l] < 1 || !w->w[l] || !w->b[l]) return fail(B2R_EINVAL, "tower_create: bad layer " + std::to_string(l));
+  if (w->widths[L - 1] > 256)
     return fail(B2R_EUNSUPPORTED, "tower_create: layer widths must be >= 1 and out_dim <= 256");
   int ndev = 0;
   B2R_CUDA(cudaGetDeviceCount(&ndev));
@@ -502,30 +511,32 @@ int b2r_tower_create(b2r_tower** out, const b2r_tower_weights* w, int device) {
   t->nnum = w->num_numerical;
   t->K1 = t->F * t->E + t->nnum;
   t->K1p = pad_to(t->K1, 64);
-  t->n[0] = w->hidden1; t->n[1] = w->hidden2; t->n[2] = w->out_dim;
-  for (int l = 0; l < 3; ++l) t->np[l] = pad_to(t->n[l], 128);
-  // the fused kernel keeps H1 (128 x N1p) in 128 KB of shared memory and all accumulators in 512 TMEM columns;
-  // its TMA output stores need 16-byte aligned rows
-  t->fused_ok = t->np[0] <= 512 && t->np[1] <= 256 && t->np[2] <= 256 && (t->n[2] % 4) == 0;
+  t->L = L;
+  for (int l = 0; l < L; ++l) {
+    t->n[l] = w->widths[l];
+    t->np[l] = pad_to(t->n[l], 128);
+  }
+  // the fused kernel is the two-hidden-layer chain: it keeps H1 (128 x N1p) in 128 KB of shared memory and all
+  // accumulators in 512 TMEM columns; its TMA output stores need 16-byte aligned rows
+  t->fused_ok = L == 3 && t->np[0] <= 512 && t->np[1] <= 256 && t->np[2] <= 256 && (t->n[2] % 4) == 0;
   memset(t->bias_host, 0, sizeof(t->bias_host));
-  const int kin[3] = {t->K1, t->n[0], t->n[1]};
-  const int kp[3] = {t->K1p, t->np[0], t->np[1]};
-  const float* W[3] = {w->w1, w->w2, w->w3};
-  const float* Bv[3] = {w->b1, w->b2, w->b3};
   int rc = B2R_OK;
   float wmax = 0.f;
   int boff = 0;
-  for (int l = 0; l < 3 && rc == B2R_OK; ++l) {
-    std::vector<uint16_t> wh((size_t)t->np[l] * kp[l], 0), wbf((size_t)t->np[l] * kp[l], 0);
+  for (int l = 0; l < L && rc == B2R_OK; ++l) {
+    const int kin = l == 0 ? t->K1 : t->n[l - 1];
+    const int kp = l == 0 ? t->K1p : t->np[l - 1];
+    const float* W = w->w[l];
+    std::vector<uint16_t> wh((size_t)t->np[l] * kp, 0), wbf((size_t)t->np[l] * kp, 0);
     std::vector<float> bb((size_t)t->np[l], 0.f);
     for (int o = 0; o < t->n[l]; ++o) {
-      for (int i = 0; i < kin[l]; ++i) {
-        const float v = W[l][(size_t)o * kin[l] + i];
+      for (int i = 0; i < kin; ++i) {
+        const float v = W[(size_t)o * kin + i];
         if (!(fabsf(v) <= wmax)) wmax = fabsf(v);   // NaN propagates into wmax
-        wh[(size_t)o * kp[l] + i] = f32_to_f16_sat(v);
-        wbf[(size_t)o * kp[l] + i] = f32_to_bf16(v);
+        wh[(size_t)o * kp + i] = f32_to_f16_sat(v);
+        wbf[(size_t)o * kp + i] = f32_to_bf16(v);
       }
-      bb[o] = Bv[l][o];
+      bb[o] = w->b[l][o];
     }
     if (t->fused_ok) memcpy(t->bias_host + boff, bb.data(), bb.size() * 4);
     boff += t->np[l];
@@ -538,10 +549,10 @@ int b2r_tower_create(b2r_tower** out, const b2r_tower_weights* w, int device) {
     cudaMemcpy(t->wb[l], wbf.data(), wbf.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(t->b[l], bb.data(), bb.size() * 4, cudaMemcpyHostToDevice);
     const int bn = (t->np[l] % 256 == 0) ? 256 : 128;
-    rc = make_tmap_f16_2d(&t->tmW[l], t->w[l], t->np[l], kp[l], bn);
-    if (!rc) rc = make_tmap_f16_2d(&t->tmWb[l], t->wb[l], t->np[l], kp[l], bn);
-    if (!rc) rc = make_tmap_f16_2d(&t->tmWf[l], t->w[l], t->np[l], kp[l], 128);
-    if (!rc) rc = make_tmap_f16_2d(&t->tmWfb[l], t->wb[l], t->np[l], kp[l], 128);
+    rc = make_tmap_f16_2d(&t->tmW[l], t->w[l], t->np[l], kp, bn);
+    if (!rc) rc = make_tmap_f16_2d(&t->tmWb[l], t->wb[l], t->np[l], kp, bn);
+    if (!rc && t->fused_ok) rc = make_tmap_f16_2d(&t->tmWf[l], t->w[l], t->np[l], kp, 128);
+    if (!rc && t->fused_ok) rc = make_tmap_f16_2d(&t->tmWfb[l], t->wb[l], t->np[l], kp, 128);
   }
   // a BN-folded weight outside the fp16 range (tiny running_var, huge gamma): bf16 operands from the start
   if (!(wmax <= 65504.f)) t->bf16 = 1;
@@ -560,6 +571,27 @@ int b2r_tower_create(b2r_tower** out, const b2r_tower_weights* w, int device) {
   }
   *out = t;
   return B2R_OK;
+}
+
+int b2r_tower_create(b2r_tower** out, const b2r_tower_weights* w, int device) {
+  if (!out || !w) return fail(B2R_EINVAL, "tower_create: NULL argument");
+  *out = nullptr;
+  if (w->hidden1 < 1 || w->hidden2 < 1 || w->out_dim < 1 || w->out_dim > 256)
+    return fail(B2R_EUNSUPPORTED, "tower_create: layer widths must be >= 1 and out_dim <= 256");
+  const int widths[3] = {w->hidden1, w->hidden2, w->out_dim};
+  const float* W[3] = {w->w1, w->w2, w->w3};
+  const float* Bv[3] = {w->b1, w->b2, w->b3};
+  b2r_tower_layers lw;
+  lw.num_fields = w->num_fields;
+  lw.emb_dim = w->emb_dim;
+  lw.num_numerical = w->num_numerical;
+  lw.num_layers = 3;
+  lw.cards = w->cards;
+  lw.tables = w->tables;
+  lw.widths = widths;
+  lw.w = W;
+  lw.b = Bv;
+  return b2r_tower_create_layers(out, &lw, device);
 }
 
 int b2r_tower_set_param(b2r_tower* t, const char* name, double value) {
@@ -598,10 +630,8 @@ static bool tower_uses_fused(const b2r_tower* t) {
 size_t b2r_tower_workspace(const b2r_tower* t, int64_t B) {
   if (!t || B <= 0) return 0;
   if (tower_uses_fused(t)) return 0;     // the fused kernel keeps every intermediate on the SM
-  size_t s = 0;
-  s += align_up((size_t)B * t->K1p * 2, 256);
-  s += align_up((size_t)B * t->np[0] * 2, 256);
-  s += align_up((size_t)B * t->np[1] * 2, 256);
+  size_t s = align_up((size_t)B * t->K1p * 2, 256);               // gathered layer-1 operand
+  for (int l = 0; l + 1 < t->L; ++l) s += align_up((size_t)B * t->np[l] * 2, 256);   // one buffer per hidden layer
   return s;
 }
 
@@ -626,10 +656,9 @@ int b2r_tower_forward(b2r_tower* t, const int64_t* cat, const float* num, int64_
     return fail(B2R_ENOMEM, "tower_forward: workspace too small");
   }
   const bool bf = t->bf16 != 0;
+  const int L = t->L;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   __half* a1 = reinterpret_cast<__half*>(ws);
-  __half* h1 = reinterpret_cast<__half*>(ws + align_up((size_t)B * t->K1p * 2, 256));
-  __half* h2 = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(h1) + align_up((size_t)B * t->np[0] * 2, 256));
   int rc = B2R_OK;
   {
     int64_t blocks = ceil_div(B, kGatherWarps);
@@ -645,34 +674,19 @@ int b2r_tower_forward(b2r_tower* t, const int64_t* cat, const float* num, int64_
     if (e != cudaSuccess) rc = fail(B2R_ECUDA, std::string("launch tower_gather_f16_kernel: ") + cudaGetErrorString(e));
     else count_launch();
   }
-  const __half* act[3] = {a1, h1, h2};
-  const int kp[3] = {t->K1p, t->np[0], t->np[1]};
-  void* outs[3] = {h1, h2, out};
-  for (int l = 0; l < 3 && rc == B2R_OK; ++l) {
-    CUtensorMap tmA;
-    rc = make_tmap_f16_2d(&tmA, act[l], B, kp[l], 128);
-    if (rc) break;
+  // one GEMM launch per Linear: hidden layers write their ReLU'd 16-bit activations (padded columns are
+  // relu(0 + 0) = 0, so they contribute nothing as the next layer's K padding); the last one normalises
+  const void* act = a1;
+  uint8_t* next = ws + align_up((size_t)B * t->K1p * 2, 256);
+  for (int l = 0; l < L && rc == B2R_OK; ++l) {
+    const bool last = l == L - 1;
+    const int kp = l == 0 ? t->K1p : t->np[l - 1];
     const CUtensorMap& tmW = bf ? t->tmWb[l] : t->tmW[l];
-    GemmParams gp;
-    gp.M = B;
-    gp.N = t->np[l];
-    gp.K = kp[l];
-    gp.bias = t->b[l];
-    gp.out = outs[l];
-    gp.ldo = (l == 2) ? t->n[2] : t->np[l];
-    gp.n_store = (l == 2) ? t->n[2] : t->np[l];
-    gp.mode = (l == 2) ? 1 : 0;
-    gp.err_flag = err_flag;
-    if (l == 2 && t->np[2] > 256) { rc = fail(B2R_EUNSUPPORTED, "tower_forward: out_dim > 256"); break; }
-    if (l == 2) {
-      // the normalising epilogue needs the whole output row in one tile
-      if (t->np[2] == 256) rc = launch_gemm<256>(tmA, tmW, gp, t->num_sms, stream, bf);
-      else rc = launch_gemm<128>(tmA, tmW, gp, t->num_sms, stream, bf);
-    } else if (t->np[l] % 256 == 0) {
-      rc = launch_gemm<256>(tmA, tmW, gp, t->num_sms, stream, bf);
-    } else {
-      rc = launch_gemm<128>(tmA, tmW, gp, t->num_sms, stream, bf);
-    }
+    rc = launch_linear(act, tmW, B, t->np[l], kp, t->b[l], last ? (void*)out : (void*)next,
+                       last ? t->n[l] : t->np[l], last ? t->n[l] : t->np[l], last ? 1 : 0, err_flag, t->num_sms,
+                       stream, bf);
+    act = next;
+    next += align_up((size_t)B * t->np[l] * 2, 256);
   }
   if (prev != t->device) cudaSetDevice(prev);
   return rc;

@@ -214,26 +214,23 @@ class _Tower(nn.Module):
         self._free()
         lib = _lib.load()
         folded = fold_tower_weights(self.mlp)
-        if len(folded) != 3:
-            raise NotImplementedError("the B200 tower kernel implements exactly two hidden layers "
-                                      f"(hidden_dims of length 2); got {len(folded) - 1}")
         tables = [e.weight for e in self.embedding_layer.embeddings.values()]
         for w in tables:
             if w.device != device or w.dtype != torch.float32 or not w.is_contiguous():
                 raise RuntimeError("move the tower to the input's CUDA device first (.to(device))")
         F = len(tables)
+        L = len(folded)     # len(hidden_dims) + 1: any depth (reference two_tower_model.py:83-95 loops over the list)
         cards = (C.c_int64 * F)(*[w.shape[0] for w in tables])
         ptrs = (C.c_void_p * F)(*[w.data_ptr() for w in tables])
-        (w1, b1), (w2, b2), (w3, b3) = folded
-        tw = _lib.TowerWeights(
+        tw = _lib.TowerLayers(
             num_fields=F, emb_dim=self.embedding_layer.embedding_dim, num_numerical=self._numerical_dim,
-            hidden1=w1.shape[0], hidden2=w2.shape[0], out_dim=w3.shape[0],
-            cards=cards, tables=ptrs,
-            w1=w1.ctypes.data, b1=b1.ctypes.data, w2=w2.ctypes.data, b2=b2.ctypes.data,
-            w3=w3.ctypes.data, b3=b3.ctypes.data)
+            num_layers=L, cards=cards, tables=ptrs,
+            widths=(C.c_int * L)(*[w.shape[0] for w, _ in folded]),
+            w=(C.c_void_p * L)(*[w.ctypes.data for w, _ in folded]),
+            b=(C.c_void_p * L)(*[b.ctypes.data for _, b in folded]))
         h = C.c_void_p()
         with torch.cuda.device(device):
-            _lib.check(lib.b2r_tower_create(C.byref(h), C.byref(tw), device.index or 0))
+            _lib.check(lib.b2r_tower_create_layers(C.byref(h), C.byref(tw), device.index or 0))
             if self.operand_dtype is not None:
                 _lib.check(lib.b2r_tower_set_param(h, b"operand_dtype", {"fp16": 0.0, "bf16": 1.0}[self.operand_dtype]))
             if self.force_path:

@@ -23,7 +23,10 @@ BATCH = 48
 
 
 def main():
+    only = sys.argv[1:]        # `python make_golden.py deep3 one_hidden` regenerates just those fixtures
     for name, cfg in CONFIGS.items():
+        if only and name not in only:
+            continue
         user, ad = feature_dims(cfg)
         model = ref.TwoTowerModel(user_feature_dims=user, ad_feature_dims=ad, numerical_dim=cfg["numerical_dim"],
                                   embedding_dim=cfg["embedding_dim"], hidden_dims=cfg["hidden_dims"],

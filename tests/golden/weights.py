@@ -2,7 +2,7 @@
 
 `make_state(cfg, seed)` returns {state_dict key: np.ndarray} for a TwoTowerModel with the
 reference's key names (two_tower_model.py: `user_tower.embedding_layer.embeddings.<f>.weight`,
-`user_tower.mlp.{0,1,4,5,8}.*`, same for `ad_tower`).  Used by make_golden.py (loaded into the
+`user_tower.mlp.{0,1,4,5,8}.*` for two hidden layers, same for `ad_tower`).  Used by make_golden.py (loaded into the
 REFERENCE model to produce expected outputs) and by the tests (loaded into the oracle and into
 the B200 modules), so the fixture only has to store inputs and expected outputs.
 """
@@ -18,7 +18,21 @@ CONFIGS = {
     # tutorial.ipynb shape
     "small": dict(user_cards=[30, 20, 10, 5, 30, 7], ad_cards=[11, 7, 5, 3] * 5,
                   numerical_dim=13, embedding_dim=16, hidden_dims=[256, 128], output_dim=128),
+    # `hidden_dims` of other lengths (train.py:350 --hidden_dims nargs='+'; two_tower_model.py:83-95 loops over it)
+    "deep3": dict(user_cards=[30, 20, 10, 5], ad_cards=[11, 7, 5, 3, 9],
+                  numerical_dim=13, embedding_dim=16, hidden_dims=[384, 200, 128], output_dim=64),
+    "one_hidden": dict(user_cards=[30, 20, 10, 5], ad_cards=[11, 7, 5, 3, 9],
+                       numerical_dim=13, embedding_dim=16, hidden_dims=[192], output_dim=96),
+    "no_hidden": dict(user_cards=[30, 20, 10, 5], ad_cards=[11, 7, 5, 3, 9],
+                      numerical_dim=13, embedding_dim=8, hidden_dims=[], output_dim=32),
+    # two hidden layers too wide for the fused kernel (layer-by-layer launches)
+    "wide2": dict(user_cards=[30, 20, 10, 5], ad_cards=[11, 7, 5, 3, 9],
+                  numerical_dim=13, embedding_dim=16, hidden_dims=[640, 384], output_dim=256),
+    # widths that are not multiples of anything convenient (output rows not 16-byte aligned)
+    "odd_out": dict(user_cards=[30, 20, 10, 5], ad_cards=[11, 7, 5, 3, 9],
+                    numerical_dim=13, embedding_dim=16, hidden_dims=[100, 60], output_dim=50),
 }
+DEPTH_CONFIGS = ["deep3", "one_hidden", "no_hidden", "wide2", "odd_out"]
 
 
 def feature_dims(cfg):

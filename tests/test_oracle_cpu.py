@@ -5,12 +5,12 @@ import pytest
 from oracle import towers as otowers
 from oracle.compare import compare_topk, recall_at_k
 from oracle.flat import NEG_FLT_MAX, OracleFAISSIndex, OracleIndexFlatIP, normalize_L2, topk_desc
-from weights import CONFIGS, make_inputs, make_state
+from weights import CONFIGS, DEPTH_CONFIGS, make_inputs, make_state
 
 GOLDEN = __import__("pathlib").Path(__file__).parent / "golden"
 
 
-@pytest.mark.parametrize("cfg_name", ["cfg1", "small"])
+@pytest.mark.parametrize("cfg_name", ["cfg1", "small"] + DEPTH_CONFIGS)
 def test_oracle_towers_match_reference_golden(cfg_name):
     """oracle/towers.py vs outputs of the reference's own two_tower_model.py."""
     fx = np.load(GOLDEN / f"towers_{cfg_name}.npz")

@@ -47,6 +47,41 @@ def test_towers_match_reference_golden(built_lib, cfg_name):
     assert np.array_equal(u2.cpu().numpy(), u) and np.array_equal(a2.cpu().numpy(), a)
 
 
+@pytest.mark.parametrize("cfg_name", ["deep3", "one_hidden", "no_hidden", "wide2", "odd_out"])
+def test_hidden_dims_of_any_length_match_reference_golden(built_lib, cfg_name):
+    """`hidden_dims` with 0, 1, 3 entries, two entries too wide for the fused kernel, and widths that are not
+    multiples of 4 (reference two_tower_model.py:83-95 builds one block per entry; train.py:350 exposes it):
+    gather + one tcgen05 GEMM launch per Linear, against outputs of the reference's own module."""
+    import torch
+    from oracle import towers as otowers
+    from weights import make_inputs
+    m, fx, cfg, state = _model(cfg_name)
+    ucat, unum, acat = (torch.from_numpy(fx[k]).cuda() for k in ("ucat", "unum", "acat"))
+    with torch.no_grad():
+        assert np.array_equal(m.user_tower.embedding_layer(ucat).cpu().numpy(), fx["user_embedding_layer"])
+        u = m.get_user_embeddings(ucat, unum).cpu().numpy()
+        a = m.get_ad_embeddings(acat).cpu().numpy()
+    assert m.user_tower._handle is not None
+    from movie_recommender_demo_b200 import _lib
+    assert _lib.load().b2r_tower_get_param(m.user_tower._handle, b"fused") == 0.0
+    assert u.shape == fx["user_out"].shape and a.shape == fx["ad_out"].shape
+    assert np.abs(u - fx["user_out"]).max() < TOWER_ATOL, np.abs(u - fx["user_out"]).max()
+    assert np.abs(a - fx["ad_out"]).max() < TOWER_ATOL, np.abs(a - fx["ad_out"]).max()
+    # a batch that is not a multiple of the 128-row tile, against the oracle (pinned to the same goldens)
+    ucat2, unum2, acat2 = make_inputs(cfg, 91, 333)
+    with torch.no_grad():
+        u2 = m.get_user_embeddings(torch.from_numpy(ucat2).cuda(), torch.from_numpy(unum2).cuda()).cpu().numpy()
+        a2 = m.get_ad_embeddings(torch.from_numpy(acat2).cuda()).cpu().numpy()
+    assert np.abs(u2 - otowers.tower_forward(state, "user_tower", ucat2, unum2)).max() < TOWER_ATOL
+    assert np.abs(a2 - otowers.tower_forward(state, "ad_tower", acat2)).max() < TOWER_ATOL
+    # the bf16 operand format on the same towers (what a saturating checkpoint switches to): 8x coarser rounding
+    m.user_tower.operand_dtype = "bf16"
+    m.user_tower._free()
+    with torch.no_grad():
+        ub = m.get_user_embeddings(ucat, unum).cpu().numpy()
+    assert np.abs(ub - fx["user_out"]).max() < 2e-2
+
+
 @pytest.mark.parametrize("B", [1, 2, 127, 128, 129, 1000, 4099])
 def test_tower_batch_sizes_vs_oracle(built_lib, B):
     import torch
