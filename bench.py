@@ -452,6 +452,67 @@ def run_extras(args, torch, dev, peaks, flat_index, q_dev, emit_err):
         out["operand_dtype"] = m.native_operand_dtype
         return out
     guarded("stage2_ranker", ranker)
+
+    # ---- the reference's production request (inference.py:199-288): ONE user dict on the host -> preprocess ->
+    #      user tower -> top-500 over the 1M-row corpus -> Stage-2 ranker over the 500 candidates -> top-10 on the
+    #      host.  Wall-clock per request through AdRecommenderInference.recommend_ads (encode + search end to end).
+    def request():
+        sys.path.insert(0, str(ROOT / "tests" / "golden"))
+        from weights import CONFIGS, RANKER_CONFIGS, feature_dims, make_ranker_state, make_state
+        from movie_recommender_demo_b200.inference import AdRecommenderInference
+        from movie_recommender_demo_b200.transformer_ranker import TransformerRanker
+        from movie_recommender_demo_b200.two_tower_model import TwoTowerModel
+        cfg, rcfg = CONFIGS["cfg1"], RANKER_CONFIGS["cfg1"]
+        user, ad = feature_dims(cfg)
+        tt = TwoTowerModel(user, ad, cfg["numerical_dim"], cfg["embedding_dim"], cfg["hidden_dims"], cfg["output_dim"])
+        tt.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in make_state(cfg, 1).items()})
+        ruser, rad = feature_dims(rcfg)
+        rk = TransformerRanker(ruser, rad, rcfg["numerical_dim"], embedding_dim=rcfg["embedding_dim"],
+                               d_model=rcfg["d_model"], num_heads=rcfg["num_heads"], num_layers=rcfg["num_layers"],
+                               d_ff=rcfg["d_ff"])
+        rk.load_state_dict({k: torch.from_numpy(v) for k, v in make_ranker_state(rcfg, 1).items()})
+
+        class _Enc:                      # duck-typed fitted LabelEncoder / StandardScaler of the reference's
+            def __init__(self, n):       # CriteoDataPreprocessor (CPU ETL, out of scope)
+                self.classes_ = np.array([f"v{j}" for j in range(n - 1)] + ["missing"], dtype=object)
+
+        class _Pre:
+            feature_dims = {**user, **ad}
+            label_encoders = {c: _Enc(n) for c, n in {**user, **ad}.items()}
+            numerical_cols = [f"I{i + 1}" for i in range(cfg["numerical_dim"])]
+
+            class scaler:
+                @staticmethod
+                def transform(x):
+                    return np.asarray(x, dtype=np.float32)
+
+        users = [{"categorical": {f"C{i + 1}": f"v{(7 * u + i) % 40}" for i in range(6)},
+                  "numerical": {f"I{i + 1}": float(u % 17 + i) for i in range(cfg["numerical_dim"])}} for u in range(64)]
+        out = {"workload": f"AdRecommenderInference.recommend_ads, one request: host dict -> user tower -> Flat top-{K_TOP} "
+                           f"over {flat_index.index.ntotal}x{D} -> Stage-2 ranker on {K_TOP} candidates -> top-10 on the host",
+               "unit": "ms per request (wall clock, host to host)"}
+        for name, ranker_mod in (("stage1_only", None), ("two_stage", rk)):
+            inf = AdRecommenderInference(model_dir="/nonexistent", device=str(dev), preprocessor=_Pre(),
+                                         two_tower_model=tt, transformer_ranker=ranker_mod, faiss_index=flat_index,
+                                         verbose=False)
+            for u in users[:8]:
+                inf.recommend_ads(u, top_k=10, stage1_k=K_TOP)
+            lat, s1, s2 = [], [], []
+            for r in range(200):
+                t0 = time.perf_counter()
+                rec = inf.recommend_ads(users[r % 64], top_k=10, stage1_k=K_TOP)
+                lat.append((time.perf_counter() - t0) * 1e3)
+                s1.append(rec["timing"]["stage1_ms"])
+                s2.append(rec["timing"]["stage2_ms"])
+            t0 = time.perf_counter()
+            inf.batch_recommend(users, top_k=10, stage1_k=K_TOP)
+            b64 = (time.perf_counter() - t0) * 1e3
+            out[name] = {"median_ms": float(np.median(lat)), "p99_ms": float(np.percentile(lat, 99)),
+                         "stage1_median_ms": float(np.median(s1)), "stage2_median_ms": float(np.median(s2)),
+                         "batch_recommend_64_users_ms": b64, "requests_per_s_serial": 1e3 / float(np.median(lat))}
+        out["value"] = out["two_stage"]["median_ms"]
+        return out
+    guarded("recommend_request", request)
     return extra
 
 
