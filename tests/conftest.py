@@ -16,9 +16,9 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def built_lib():
-    """libb2retr.so, built in-tree if missing (nvcc cross-compiles without a GPU)."""
+    """libb2retr.so, (re)built in-tree when missing or older than a source / header (incremental: a no-op when
+    up to date; nvcc cross-compiles without a GPU) - a stale library must never be what the tests load."""
     from movie_recommender_demo_b200 import _lib
-    if not _lib.LIB_PATH.exists():
-        from movie_recommender_demo_b200.build import build
-        build()
+    from movie_recommender_demo_b200.build import build
+    build()
     return _lib.load()
