@@ -282,20 +282,29 @@ def parity_by_regeneration(torch, dev, total_rows, q_np, ids, dist, nq=8):
 
 
 # ------------------------------------------------------------------------------- extra configs (N = 1)
-def run_extras(args, torch, dev, peaks, flat_index, q_dev, emit_err):
-    """BASELINE configs other than the headline, one sub-result each (value + roofline)."""
+def run_extras(args, torch, dev, peaks, flat_index, q_dev, emit_err, skip=(), progress=None):
+    """BASELINE configs other than the headline, one sub-result each (value + roofline).  `skip`: names not to
+    run; `progress(name, extra)` is called before (name) and after (None) every sub-result so that the caller can
+    persist what is finished."""
     import numpy as np
     from movie_recommender_demo_b200.faiss_retrieval import FAISSIndex, IndexFlatIP
     extra = {}
     hbm = peaks["hbm_gbs"]
 
     def guarded(name, fn):
+        if name in skip:
+            return
+        if progress:
+            progress(name, extra)
         try:
             extra[name] = fn()
         except Exception as exc:  # report, never hide; the headline line must still be printed
             extra[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
             emit_err(f"extra {name} failed: {exc!r}")
         torch.cuda.empty_cache()
+        torch.cuda.synchronize()      # a sticky device error surfaces HERE, attributed to this sub-result
+        if progress:
+            progress(None, extra)
 
     # ---- configs[1] at the memory-bound batches
     def flat_small(Q):
@@ -545,6 +554,106 @@ def run_anchor(args, torch, dev, peaks):
     return out
 
 
+EXTRA_NAMES = ["flat_q1", "flat_q64", "flat_clustered", "ivf_10M", "ivfpq_10M", "tower_65536", "stage2_ranker",
+               "recommend_request", "flat_100M_one_gpu"]
+
+
+def run_extras_isolated(args, emit_err, timeout_s=900):
+    """Run the sub-results in a child `bench.py --extras-child FILE`.  The child rewrites FILE after every
+    sub-result; when it dies (device fault, OOM kill, timeout) the sub-result it was on is recorded as an error
+    and a new child carries on with the rest."""
+    import tempfile
+    extra = {}
+    skip = ["flat_100M_one_gpu"] if args.no_anchor else []
+    fd, path = tempfile.mkstemp(prefix="b2r_extras_", suffix=".json")
+    os.close(fd)
+    try:
+        for attempt in range(4):
+            if all(n in skip for n in EXTRA_NAMES):
+                break
+            Path(path).write_text("{}")
+            cmd = [sys.executable, str(ROOT / "bench.py"), "--extras-child", path, "--extras-skip", ",".join(skip),
+                   "--batch", str(args.batch), "--scan-dtype", args.scan_dtype]
+            env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+            try:
+                r = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=timeout_s, env=env)
+                rc, err_tail = r.returncode, (r.stderr or "")[-400:]
+            except subprocess.TimeoutExpired as exc:
+                rc, err_tail = -9, f"timed out after {timeout_s} s: " + str(exc.stderr or "")[-300:]
+            try:
+                state = json.loads(Path(path).read_text() or "{}")
+            except Exception:
+                state = {}
+            extra.update(state.get("done", {}))
+            skip += [n for n in state.get("done", {}) if n not in skip]
+            running = state.get("running")
+            if rc == 0 and not running:
+                break
+            if running and running not in extra:
+                extra[running] = {"error": f"the child process running this sub-result died (rc {rc}): {err_tail}"[:600]}
+                emit_err(f"extra {running}: child died with rc {rc}; continuing with the rest in a new process")
+                skip.append(running)
+            elif not running:      # died before / between sub-results: do not loop on it
+                emit_err(f"extras child failed with rc {rc}: {err_tail}")
+                extra.setdefault("_child_error", f"rc {rc}: {err_tail}"[:600])
+                break
+    finally:
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+    return {n: extra[n] for n in EXTRA_NAMES if n in extra} | {k: v for k, v in extra.items() if k not in EXTRA_NAMES}
+
+
+def run_extras_child(args):
+    """Child side of run_extras_isolated: same 1M-row corpus as the headline, then every sub-result not skipped."""
+    import torch
+    from movie_recommender_demo_b200.faiss_retrieval import FAISSIndex
+    os.dup2(2, 1)                      # native banners must not reach the parent's JSON stream
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    peaks = _peaks()
+    FAISSIndex.verbose = False
+    skip = [n for n in args.extras_skip.split(",") if n]
+    path = Path(args.extras_child)
+    state = {"done": {}, "running": None}
+
+    def save():
+        tmp = path.with_suffix(".tmp")
+        tmp.write_text(json.dumps(state))
+        os.replace(tmp, path)
+
+    def progress(name, extra):
+        state["running"] = name
+        state["done"] = dict(extra)
+        save()
+
+    def emit_err(msg):
+        sys.stderr.write(f"[bench extras] {msg}\n")
+
+    index = FAISSIndex(D, 'Flat', device=0)
+    index.index.reserve(CORPUS_1GPU)
+    if args.scan_dtype != "auto":
+        index.index.set_param("scan_dtype", {"bf16": 0, "fp16": 1}[args.scan_dtype])
+    g = torch.Generator(device=dev)
+    for c in range((CORPUS_1GPU + CHUNK - 1) // CHUNK):
+        index.add(_chunk_rows(torch, dev, g, c)[: min(CHUNK, CORPUS_1GPU - c * CHUNK)])
+    torch.cuda.synchronize()
+    q_dev_extra = torch.randn((max(args.batch, 64), D), generator=torch.Generator().manual_seed(2)).to(dev)
+    extra = run_extras(args, torch, dev, peaks, index, q_dev_extra, emit_err, skip=skip, progress=progress)
+    del index
+    torch.cuda.empty_cache()
+    if "flat_100M_one_gpu" not in skip:
+        progress("flat_100M_one_gpu", extra)
+        try:
+            extra["flat_100M_one_gpu"] = run_anchor(args, torch, dev, peaks)
+        except Exception as exc:
+            extra["flat_100M_one_gpu"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        torch.cuda.synchronize()
+        progress(None, extra)
+    return 0
+
+
 # ------------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     import numpy as np
@@ -780,19 +889,15 @@ def run_b200(args):
 
     # ---- the other BASELINE configs + the single-GPU anchor of the sharded workload (N = 1 only)
     extra = None
+    scan_fp16 = int(flat.get_param("scan_dtype")) == 1
     if world == 1 and rank == 0 and not args.no_extra and total_rows == CORPUS_1GPU:
-        extra = run_extras(args, torch, dev, peaks, index, q_dev_extra, emit_err)
+        # The sub-results run in CHILD processes: a device fault in one of them (a sticky CUDA error kills every
+        # later call of its process) must not cost the headline measurement above, nor the other sub-results.
         del index, flat
         torch.cuda.empty_cache()
-        if not args.no_anchor:
-            try:
-                extra["flat_100M_one_gpu"] = run_anchor(args, torch, dev, peaks)
-            except Exception as exc:
-                extra["flat_100M_one_gpu"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-        flat = None
+        extra = run_extras_isolated(args, emit_err)
 
     if rank == 0:
-        scan_fp16 = (int(flat.get_param("scan_dtype")) == 1) if flat is not None else (args.scan_dtype != "bf16")
         exch = None if world == 1 else exchange_mode(Q, world)
         out = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
@@ -870,9 +975,13 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the parity spot check")
     ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (N = 1)")
     ap.add_argument("--no-anchor", action="store_true", help="skip the 100M-rows-on-one-GPU anchor (N = 1)")
+    ap.add_argument("--extras-child", default="", help=argparse.SUPPRESS)   # internal: see run_extras_isolated
+    ap.add_argument("--extras-skip", default="", help=argparse.SUPPRESS)
     ap.add_argument("--scan-dtype", choices=["auto", "bf16", "fp16"], default="auto",
                     help="16-bit format of the scan copy (auto = fp16 for L2-normalised corpora)")
     args = ap.parse_args()
+    if args.extras_child:
+        return run_extras_child(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

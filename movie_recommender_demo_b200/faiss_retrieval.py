@@ -305,10 +305,15 @@ class _DeviceIndex:
         torch = self._torch
         with torch.cuda.device(self.device):
             need = int(self._lib.b2r_index_search_workspace(self._h, nq, k, nprobe))
+            # I | D | status live in ONE buffer (labels first: 8-byte aligned) so that the result leaves for the
+            # host in one copy instead of three
+            nI, nD = nq * k * 8, nq * k * 4
+            packed = torch.zeros(nI + nD + nq * 4, dtype=torch.uint8, device=self.device)
             ent = {"q": torch.zeros((nq, self._dp), dtype=torch.float32, device=self.device),
-                   "D": torch.empty((nq, k), dtype=torch.float32, device=self.device),
-                   "I": torch.empty((nq, k), dtype=torch.int64, device=self.device),
-                   "status": torch.zeros(nq, dtype=torch.int32, device=self.device),
+                   "packed": packed, "cuts": (nI, nI + nD),
+                   "I": packed[:nI].view(torch.int64).view(nq, k),
+                   "D": packed[nI:nI + nD].view(torch.float32).view(nq, k),
+                   "status": packed[nI + nD:].view(torch.int32),
                    "tau_retry": torch.empty(nq, dtype=torch.float32, device=self.device),
                    "ws": torch.empty(max(need, 1), dtype=torch.uint8, device=self.device)}
 
@@ -375,16 +380,19 @@ class _DeviceIndex:
             ent["graph"].replay()
             self.replayed_launches += ent["launches"]
             D, I = ent["D"], ent["I"]
-            st_h, D_h, I_h = self._to_pinned(ent["status"]), self._to_pinned(D), self._to_pinned(I)
+            nq = q.shape[0]
+            cI, cD = ent["cuts"]
+            host = self._to_pinned(ent["packed"])      # labels | distances | status in one async copy
             torch.cuda.current_stream(self.device).synchronize()
-            st = st_h.numpy()
+            st = host[cD:].view(torch.int32).numpy()
             if (st & _RETRY_BITS).any() and self._supports_retry:
                 st = self._retry(q, k, normalize, nprobe, st.copy(), ent["tau_retry"], D, I, None, None)
-                D_h, I_h = self._to_pinned(D), self._to_pinned(I)
+                host = self._to_pinned(ent["packed"])
                 torch.cuda.current_stream(self.device).synchronize()
         self.last_status = st
         self._warn_status(st)
-        return D_h.numpy(), I_h.numpy()
+        return (host[cI:cD].view(torch.float32).view(nq, int(k)).numpy(),
+                host[:cI].view(torch.int64).view(nq, int(k)).numpy())
 
     def _search_pipelined(self, qt, k, normalize, nprobe):
         """Large batches: search in chunks of _PIPE_CHUNK queries and copy each chunk's results to

@@ -149,9 +149,11 @@ class AdRecommenderInference:
 
     # ------------------------------------------------------------------ inference
     def _stage1(self, user_categorical, user_numerical, stage1_k):
+        cat_dev = user_categorical.to(self.device)
+        num_dev = user_numerical.to(self.device, dtype=torch.float32)
+        self._dev_inputs = (user_categorical, user_numerical, cat_dev, num_dev)   # stage 2 reuses the uploads
         with torch.no_grad():
-            user_emb = self.two_tower_model.get_user_embeddings(
-                user_categorical.to(self.device), user_numerical.to(self.device, dtype=torch.float32))
+            user_emb = self.two_tower_model.get_user_embeddings(cat_dev, num_dev)
         return self.faiss_index.search(user_emb, k=stage1_k)   # CUDA tensor in, numpy (ids, scores) out
 
     def _stage2_batch(self, user_categorical, user_numerical, candidate_ids, top_k, return_scores):
@@ -161,21 +163,33 @@ class AdRecommenderInference:
         U, stage1_k = candidate_ids.shape[0], candidate_ids.shape[1]
         if self.transformer_ranker is None:
             return [(np.arange(min(top_k, stage1_k)), None) for _ in range(U)]
-        batch_user_cat = user_categorical.to(self.device).repeat_interleave(stage1_k, dim=0)
-        batch_user_num = user_numerical.to(self.device).repeat_interleave(stage1_k, dim=0)
+        held = getattr(self, "_dev_inputs", None)
+        if held is not None and held[0] is user_categorical and held[1] is user_numerical:
+            cat_dev, num_dev = held[2], held[3]           # uploaded by stage 1 of this request
+        else:
+            cat_dev = user_categorical.to(self.device)
+            num_dev = user_numerical.to(self.device, dtype=torch.float32)
+        # every user's features repeated once per candidate (the reference's `.repeat(stage1_k, 1)`, :242-243)
+        batch_user_cat = cat_dev[:, None, :].expand(U, stage1_k, cat_dev.shape[1]).reshape(U * stage1_k, -1)
+        batch_user_num = num_dev[:, None, :].expand(U, stage1_k, num_dev.shape[1]).reshape(U * stage1_k, -1)
         # the reference scores RANDOM ad features here (inference.py:246-248): one draw per user, in user order,
-        # from the global CPU generator - kept as is, so a seeded run consumes the same random stream
-        batch_ad_cat = torch.cat([torch.randint(0, 200, (stage1_k, 20)).long() for _ in range(U)]).to(self.device)
+        # from the global CPU generator.  ONE draw of U * stage1_k rows consumes the same random stream as U draws
+        # of stage1_k rows (the CPU generator fills element by element; tests/test_host_logic_cpu.py checks it),
+        # so a seeded run sees the numbers the reference's loop would see.
+        batch_ad_cat = torch.randint(0, 200, (U * stage1_k, 20)).to(self.device)
+        tasks = ('ctr', 'engagement', 'revenue')
         with torch.no_grad():
             pred = self.transformer_ranker(batch_user_cat, batch_ad_cat, batch_user_num)
-        sig = {t: torch.sigmoid(pred[t]).reshape(U, stage1_k).cpu().numpy() for t in ('ctr', 'engagement', 'revenue')}
+            # one sigmoid launch and ONE device -> host copy for the three heads (the reference: three of each)
+            sig_all = torch.sigmoid(torch.stack([pred[t].reshape(-1) for t in tasks])).cpu().numpy()
+        sig = {t: sig_all[i].reshape(U, stage1_k) for i, t in enumerate(tasks)}
         out = []
         for u in range(U):
             ctr = sig['ctr'][u]
             order = np.argsort(ctr)[::-1][:top_k]
             scores = None
             if return_scores:
-                scores = {t: sig[t][u][order].tolist() for t in ('ctr', 'engagement', 'revenue')}
+                scores = {t: sig[t][u][order].tolist() for t in tasks}
             out.append((order, scores))
         return out
 

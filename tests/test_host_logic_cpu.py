@@ -67,3 +67,57 @@ def test_bench_b200_arm_refuses_to_run_without_a_gpu():
         pytest.skip("CPU-only check")
     r = _run_bench("--steps", "1", "--warmup", "1")
     assert r.returncode != 0 and "no CPU fallback" in r.stderr and r.stdout.strip() == ""
+
+
+def test_one_randint_draw_consumes_the_stream_of_the_per_user_draws():
+    """inference._stage2_batch draws the reference's random ad features (inference.py:246-248) for U users in ONE
+    call: the global CPU generator must hand out the numbers the reference's per-user loop would have seen."""
+    import torch
+    torch.manual_seed(1234)
+    per_user = torch.cat([torch.randint(0, 200, (500, 20)).long() for _ in range(7)])
+    after_a = torch.randint(0, 200, (3,))
+    torch.manual_seed(1234)
+    one_draw = torch.randint(0, 200, (7 * 500, 20))
+    after_b = torch.randint(0, 200, (3,))
+    assert one_draw.dtype == torch.int64
+    assert torch.equal(per_user, one_draw) and torch.equal(after_a, after_b)
+
+
+def test_bench_extras_survive_a_dying_child(monkeypatch):
+    """bench.run_extras_isolated: a sub-result whose child process dies (device fault) is recorded as an error and
+    the remaining sub-results run in a new child; the skip list grows so that nothing runs twice."""
+    import argparse
+    import importlib.util
+    import json
+    import subprocess
+    import types
+    root = __import__("pathlib").Path(__file__).resolve().parent.parent
+    spec = importlib.util.spec_from_file_location("bench_under_test", root / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    calls = []
+
+    def fake_run(cmd, **kw):
+        path = cmd[cmd.index("--extras-child") + 1]
+        skip = [n for n in cmd[cmd.index("--extras-skip") + 1].split(",") if n]
+        calls.append(skip)
+        todo = [n for n in bench.EXTRA_NAMES if n not in skip]
+        if len(calls) == 1:      # dies while running the third sub-result
+            state = {"done": {n: {"value": 1.0} for n in todo[:2]}, "running": todo[2]}
+            open(path, "w").write(json.dumps(state))
+            return types.SimpleNamespace(returncode=-6, stderr="CUDA error: unspecified launch failure")
+        state = {"done": {n: {"value": 2.0} for n in todo}, "running": None}
+        open(path, "w").write(json.dumps(state))
+        return types.SimpleNamespace(returncode=0, stderr="")
+
+    monkeypatch.setattr(subprocess, "run", fake_run)
+    args = argparse.Namespace(no_anchor=True, batch=4096, scan_dtype="auto")
+    msgs = []
+    extra = bench.run_extras_isolated(args, msgs.append)
+    names = [n for n in bench.EXTRA_NAMES if n != "flat_100M_one_gpu"]
+    assert list(extra) == names                                   # every sub-result reported, anchor skipped
+    assert extra[names[0]] == {"value": 1.0} and extra[names[1]] == {"value": 1.0}
+    assert "died" in extra[names[2]]["error"] and "launch failure" in extra[names[2]]["error"]
+    assert all(extra[n] == {"value": 2.0} for n in names[3:])
+    assert len(calls) == 2 and set(calls[1]) == {"flat_100M_one_gpu", *names[:3]}
+    assert len(msgs) == 1
