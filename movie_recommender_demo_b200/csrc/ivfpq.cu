@@ -264,7 +264,10 @@ ivfpq_scan_query_kernel(const float* __restrict__ q32, int d, const int64_t* __r
   auto bar_empty = [&](int i) { return bar0 + 8u * (kPqBufs + i); };
 
   if (tid == 0) {
-    for (int i = 0; i < kPqBufs; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), kPqConsumers); }   // one group per tile
+    // every consumer warp of BOTH groups passes every tile's barriers (only the owning group looks the tile up):
+    // with an odd ring depth a buffer alternates between the groups, and a group that waited for use u of a
+    // buffer without having seen use u-1 could be let through by the parity of a fill that has not landed yet
+    for (int i = 0; i < kPqBufs; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), kPqGroups * kPqConsumers); }
     fence_mbar_init();
   }
   for (int i = tid; i < d; i += blockDim.x) qs[i] = q32[(size_t)q * d + i];
@@ -352,8 +355,13 @@ ivfpq_scan_query_kernel(const float* __restrict__ q32, int d, const int64_t* __r
     for (int t = 0; t < 4; ++t) lb[t] = lut + pq_slot<M>(rsub, j, t);
     int k = 0;
 #pragma unroll 1
-    for (int g = grp; g < ntiles; g += kPqGroups) {
+    for (int g = 0; g < ntiles; ++g) {
       const int buf = g % kPqBufs, use = g / kPqBufs;
+      if (g % kPqGroups != grp) {      // the other group's tile: keep this warp's view of the ring in step
+        mbar_wait(bar_full(buf), (uint32_t)(use & 1), 43);
+        if (lane == 0) mbar_arrive(bar_empty(buf));
+        continue;
+      }
       while (g >= p_t0[k + 1]) ++k;
       const int row0 = (g - p_t0[k]) * T::ROWS;
       const int len = p_len[k];
