@@ -255,6 +255,13 @@ ivfpq_scan_query_kernel(const float* __restrict__ q32, int d, const int64_t* __r
   int* p_t0 = p_len + kPqMaxSlots;                                    //   first tile number (cumulative, +1),
   float* p_bias = reinterpret_cast<float*>(p_t0 + kPqMaxSlots + 2);   //   -2 <c_l, q>
   uint64_t* bars = reinterpret_cast<uint64_t*>(p_bias + kPqMaxSlots); // full[kPqBufs], empty[kPqBufs]
+  // Tiles the producer has issued so far.  With an odd ring depth a buffer alternates between the two consumer
+  // groups, so a group can reach its wait for use u of a buffer without ever having waited for use u-1 - and
+  // `try_wait.parity` cannot tell "use u landed" from "use u-1 has not landed yet" (same parity).  The producer
+  // issues use u only after use u-1 was consumed (empty barrier), so a consumer that first sees `issued > g`
+  // knows the barrier is in phase u or u+1 and the parity test is unambiguous.  (The old kernel without this
+  // check died once per ~2e9 tiles: profiles/r02_ivfpq_ring_fault_old_kernel.log.)
+  int* issued = reinterpret_cast<int*>(bars + 2 * kPqBufs);
   const int q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int dsub = d / M;
@@ -264,10 +271,8 @@ ivfpq_scan_query_kernel(const float* __restrict__ q32, int d, const int64_t* __r
   auto bar_empty = [&](int i) { return bar0 + 8u * (kPqBufs + i); };
 
   if (tid == 0) {
-    // every consumer warp of BOTH groups passes every tile's barriers (only the owning group looks the tile up):
-    // with an odd ring depth a buffer alternates between the groups, and a group that waited for use u of a
-    // buffer without having seen use u-1 could be let through by the parity of a fill that has not landed yet
-    for (int i = 0; i < kPqBufs; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), kPqGroups * kPqConsumers); }
+    for (int i = 0; i < kPqBufs; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_empty(i), kPqConsumers); }   // one group per tile
+    *issued = 0;
     fence_mbar_init();
   }
   for (int i = tid; i < d; i += blockDim.x) qs[i] = q32[(size_t)q * d + i];
@@ -322,6 +327,7 @@ ivfpq_scan_query_kernel(const float* __restrict__ q32, int d, const int64_t* __r
   __syncthreads();
   const int ntiles = p_t0[nslots];
   const uint32_t tiles_s = smem_u32(tiles);
+  const uint32_t issued_s = smem_u32(issued);
 
   if (warp == kPqGroups * kPqConsumers) {
     // ------------------------------------------------------------------ producer
@@ -344,6 +350,7 @@ ivfpq_scan_query_kernel(const float* __restrict__ q32, int d, const int64_t* __r
         mbar_arrive_expect_tx(bar_full(buf), cbytes + tbytes);
         bulk_load_1d(dst, codes + (cbyte - cskip), cbytes, bar_full(buf));
         bulk_load_1d(dst + T::CODE_BYTES, row_term + (first - tskip), tbytes, bar_full(buf));
+        st_release_shared_u32(issued_s, (uint32_t)(g + 1));
       }
     }
   } else {
@@ -355,13 +362,8 @@ ivfpq_scan_query_kernel(const float* __restrict__ q32, int d, const int64_t* __r
     for (int t = 0; t < 4; ++t) lb[t] = lut + pq_slot<M>(rsub, j, t);
     int k = 0;
 #pragma unroll 1
-    for (int g = 0; g < ntiles; ++g) {
+    for (int g = grp; g < ntiles; g += kPqGroups) {
       const int buf = g % kPqBufs, use = g / kPqBufs;
-      if (g % kPqGroups != grp) {      // the other group's tile: keep this warp's view of the ring in step
-        mbar_wait(bar_full(buf), (uint32_t)(use & 1), 43);
-        if (lane == 0) mbar_arrive(bar_empty(buf));
-        continue;
-      }
       while (g >= p_t0[k + 1]) ++k;
       const int row0 = (g - p_t0[k]) * T::ROWS;
       const int len = p_len[k];
@@ -372,6 +374,8 @@ ivfpq_scan_query_kernel(const float* __restrict__ q32, int d, const int64_t* __r
       const float* tt = reinterpret_cast<const float*>(tile + T::CODE_BYTES) + (first & 3);
       float* out = scorebuf + p_out[k] + row0;
       const float b = p_bias[k];
+      for (uint32_t spin = 0; (int)ld_acquire_shared_u32(issued_s) <= g; ++spin)
+        if (spin > (1u << 30)) __trap();        // bounded like mbar_wait: a protocol bug must not hang the GPU
       mbar_wait(bar_full(buf), (uint32_t)(use & 1), 42);
       for (int base = cw * 32; base < nrows; base += kPqConsumers * 32) {
         float a[LR];
@@ -592,13 +596,13 @@ static int launch_scan_query(b2r_index* h, int nq, const float* q32, const int64
   auto kern = ivfpq_scan_query_kernel<M>;
   constexpr int kPqBufs = PqTile<M>::BUFS;
   const size_t smem = (size_t)256 * 128 * 4 + (size_t)kPqBufs * PqTile<M>::BYTES + (size_t)h->d * 4 +
-                      (size_t)kPqMaxSlots * 28 + 16 + 2 * kPqBufs * 8;
+                      (size_t)kPqMaxSlots * 28 + 16 + 2 * kPqBufs * 8 + 16;
   static bool configured[64] = {};
   int dev = 0;
   B2R_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
     B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  256 * 128 * 4 + kPqBufs * PqTile<M>::BYTES + 1024 * 4 + kPqMaxSlots * 28 + 16 + 2 * kPqBufs * 8));
+                                  256 * 128 * 4 + kPqBufs * PqTile<M>::BYTES + 1024 * 4 + kPqMaxSlots * 28 + 16 + 2 * kPqBufs * 8 + 16));
     configured[dev & 63] = true;
   }
   // few queries: split a query's probe slots over several CTAs so that the grid still covers the SMs;

@@ -289,6 +289,16 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity,
   }
 }
 
+// release / acquire on a 32-bit shared-memory word (CTA scope): a progress counter next to an mbarrier ring
+__device__ __forceinline__ void st_release_shared_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // 128-bit shared-memory accesses by 32-bit shared-window address
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
