@@ -48,6 +48,11 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> 
     OBJ_DIR.mkdir(exist_ok=True)
     srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
     hdr_m = _deps_mtime()
+    # The objects do not travel to the GPU box (.gpurunignore) but the library does: a library that is newer than
+    # every source and header is up to date whether or not its objects are still around.
+    if (not force and not ptxas_v and LIB_PATH.exists()
+            and LIB_PATH.stat().st_mtime >= max([hdr_m] + [s.stat().st_mtime for s in srcs])):
+        return LIB_PATH
     jobs = []
     objs = []
     for src in srcs:
