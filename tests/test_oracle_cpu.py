@@ -231,3 +231,36 @@ def test_oracle_stage1_matches_the_reference_tower_golden():
     ids, dist = index.search(u, k=k)
     # the two tower implementations differ by ~1e-6 per component: order may differ inside 1e-5 score gaps only
     compare_topk(ids, dist, fx["ids"], fx["dist"], k, gap_tol=1e-5, score_rtol=0, score_atol=1e-5)
+
+
+def test_oracle_wrapper_matches_the_reference_wrapper_run_over_a_faiss_stand_in():
+    """tests/golden/wrapper_flat.npz holds what the reference's OWN `FAISSIndex` class (faiss_retrieval.py:14-256,
+    executed unmodified by make_wrapper_golden.py over a numpy stand-in for the four faiss calls of the Flat path)
+    returns: float64 input, custom + default ids, k > ntotal (labels -1 -> id_map[-1]), return_distances=False,
+    batch_search chunking, get_stats, the .metadata keys.  The oracle wrapper must reproduce all of it; the GPU
+    wrapper is compared with the oracle wrapper by tests/test_flat_gpu.py::test_wrapper_semantics."""
+    from oracle.flat import OracleFAISSIndex
+    fx = np.load(GOLDEN / "wrapper_flat.npz")
+    o = OracleFAISSIndex(64, 'Flat')
+    x1, x2, q = fx["x1"], fx["x2"], fx["q"]
+    x1c, x2c, qc = x1.copy(), x2.copy(), q.copy()
+    o.add(x1, ad_ids=fx["ids1"].tolist())
+    o.add(x2)
+    assert o.id_map == fx["id_map"].tolist() == fx["metadata_id_map"].tolist()
+    ids, dist = o.search(q[:9], k=10)
+    assert ids.dtype == fx["ids_k10"].dtype and np.array_equal(ids, fx["ids_k10"])
+    np.testing.assert_allclose(dist, fx["dist_k10"], rtol=0, atol=2e-6)
+    ids, dist = o.search(q[:3], k=520)
+    assert np.array_equal(ids, fx["ids_big"])                      # the 20 missing slots carry id_map[-1]
+    assert (ids[:, 500:] == o.id_map[-1]).all() and (dist[:, 500:] == np.float32(-3.4028234663852886e38)).all()
+    np.testing.assert_allclose(dist[:, :500], fx["dist_big"][:, :500], rtol=0, atol=2e-6)
+    assert np.array_equal(dist[:, 500:], fx["dist_big"][:, 500:])
+    assert np.array_equal(o.search(q[:4], k=6, return_distances=False), fx["ids_only"])
+    b_ids, b_dist = o.batch_search(q, k=5, batch_size=7)
+    assert np.array_equal(b_ids, fx["batch_ids"])
+    np.testing.assert_allclose(b_dist, fx["batch_dist"], rtol=0, atol=2e-6)
+    stats = o.get_stats()
+    assert list(stats.keys()) == fx["stats_keys"].tolist()
+    assert [str(v) for v in stats.values()] == fx["stats_values"].tolist()
+    assert fx["metadata_keys"].tolist() == ['dimension', 'index_type', 'nlist', 'nprobe', 'id_map']
+    assert np.array_equal(x1, x1c) and np.array_equal(x2, x2c) and np.array_equal(q, qc)   # inputs never mutated
