@@ -264,3 +264,18 @@ def test_oracle_wrapper_matches_the_reference_wrapper_run_over_a_faiss_stand_in(
     assert [str(v) for v in stats.values()] == fx["stats_values"].tolist()
     assert fx["metadata_keys"].tolist() == ['dimension', 'index_type', 'nlist', 'nprobe', 'id_map']
     assert np.array_equal(x1, x1c) and np.array_equal(x2, x2c) and np.array_equal(q, qc)   # inputs never mutated
+
+
+def test_stage1_fixture_is_what_the_reference_pipeline_returns():
+    """stage1_cfg1.npz (reference towers + the ORACLE wrapper; the fixture the B200 path is compared with end to end)
+    against stage1_ref_pipeline.npz: the same system run entirely through the reference's code - its towers, its
+    FAISSIndex corpus build and its TwoStageRetriever.retrieve_and_rank, one user per call - over the numpy stand-in
+    for faiss's IndexFlatIP / normalize_L2 (make_stage1_ref_pipeline.py)."""
+    from oracle.compare import compare_topk
+    fx, ref = np.load(GOLDEN / "stage1_cfg1.npz"), np.load(GOLDEN / "stage1_ref_pipeline.npz")
+    k = int(fx["k"])
+    assert int(ref["k"]) == k and ref["ids"].shape == (int(fx["n_users"]), k)
+    # per-user (batch 1) towers vs the batched ones, sgemv vs sgemm scores: ~1e-7 apart, so order may differ
+    # inside 1e-6 gaps only
+    res = compare_topk(ref["ids"], ref["dist"], fx["ids"], fx["dist"], k, gap_tol=1e-6, score_rtol=0, score_atol=2e-6)
+    assert res["exact_positions"] >= 0.99 * ref["ids"].size
