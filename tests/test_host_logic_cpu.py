@@ -121,3 +121,38 @@ def test_bench_extras_survive_a_dying_child(monkeypatch):
     assert all(extra[n] == {"value": 2.0} for n in names[3:])
     assert len(calls) == 2 and set(calls[1]) == {"flat_100M_one_gpu", *names[:3]}
     assert len(msgs) == 1
+
+
+def test_preprocess_user_batch_matches_the_reference_method():
+    """inference.preprocess_user_batch (vectorised, dict look-ups) vs tests/golden/preprocess_users.npz = the
+    reference's own preprocess_user_features (inference.py:159-197, run by make_preprocess_golden.py over fitted
+    sklearn encoders / scaler): unseen values and absent keys fall back to 'missing' / 0, |x| is logged."""
+    import json
+    import numpy as np
+    from movie_recommender_demo_b200.inference import AdRecommenderInference
+    fx = np.load(__import__("pathlib").Path(__file__).parent / "golden" / "preprocess_users.npz")
+    users = json.loads(str(fx["users"]))
+    classes = json.loads(str(fx["classes"]))
+
+    class Enc:
+        def __init__(self, c):
+            self.classes_ = np.array(c, dtype=object)
+
+    class Scaler:
+        mean_, scale_ = fx["scaler_mean"], fx["scaler_scale"]
+
+        def transform(self, x):
+            return ((np.asarray(x, dtype=np.float64) - self.mean_) / self.scale_).astype(np.float32)
+
+    class Pre:
+        label_encoders = {c: Enc(v) for c, v in classes.items()}
+        numerical_cols = [f"I{i + 1}" for i in range(13)]
+        scaler = Scaler()
+
+    inst = object.__new__(AdRecommenderInference)      # host-side method only: no CUDA, no models
+    inst.preprocessor, inst._encoders = Pre(), None
+    cat, num = inst.preprocess_user_batch(users)
+    assert cat.dtype == __import__("torch").long and np.array_equal(cat.numpy(), fx["cat"])
+    np.testing.assert_allclose(num.numpy().astype(np.float64), fx["num"], rtol=0, atol=1e-6)
+    one_c, one_n = inst.preprocess_user_features(users[5])
+    assert np.array_equal(one_c.numpy(), fx["cat"][5:6]) and tuple(one_n.shape) == (1, 13)
