@@ -262,6 +262,34 @@ def test_wrapper_semantics(fr):
     assert np.array_equal(np.asarray(g.id_map)[I], ids[:, :5])
 
 
+def test_wrapper_matches_the_reference_wrapper_golden(fr):
+    """The B200 `FAISSIndex` against tests/golden/wrapper_flat.npz = what the reference's OWN wrapper class returns
+    (faiss_retrieval.py:14-256 executed unmodified over a numpy stand-in for faiss's IndexFlatIP / normalize_L2,
+    tests/golden/make_wrapper_golden.py): float64 input, custom then default ids, k > ntotal, ids-only return,
+    batch_search, get_stats; the caller's arrays are never written."""
+    from oracle.compare import compare_topk
+    fx = np.load(__import__("pathlib").Path(__file__).parent / "golden" / "wrapper_flat.npz")
+    x1, x2, q = fx["x1"], fx["x2"], fx["q"]
+    x1c, x2c, qc = x1.copy(), x2.copy(), q.copy()
+    g = fr.FAISSIndex(64, 'Flat')
+    g.add(x1, ad_ids=fx["ids1"].tolist())
+    g.add(x2)
+    assert list(g.id_map) == fx["id_map"].tolist()
+    ids, dist = g.search(q[:9], k=10)
+    compare_topk(ids, dist, fx["ids_k10"], fx["dist_k10"], 10, gap_tol=1e-6)
+    ids, dist = g.search(q[:3], k=520)                       # 20 slots past ntotal: id_map[-1] / -FLT_MAX
+    compare_topk(ids, dist, fx["ids_big"], fx["dist_big"], 520, gap_tol=1e-6)
+    assert (ids[:, 500:] == fx["id_map"][-1]).all() and np.array_equal(dist[:, 500:], fx["dist_big"][:, 500:])
+    only = g.search(q[:4], k=6, return_distances=False)
+    assert only.shape == (4, 6) and all(set(a) == set(b) for a, b in zip(only.tolist(), fx["ids_only"].tolist()))
+    b_ids, b_dist = g.batch_search(q, k=5, batch_size=7)
+    compare_topk(b_ids, b_dist, fx["batch_ids"], fx["batch_dist"], 5, gap_tol=1e-6)
+    stats = g.get_stats()
+    assert list(stats.keys()) == fx["stats_keys"].tolist()
+    assert [str(v) for v in stats.values()] == fx["stats_values"].tolist()
+    assert np.array_equal(x1, x1c) and np.array_equal(x2, x2c) and np.array_equal(q, qc)
+
+
 def test_accepts_cuda_tensors_and_empty_inputs(fr):
     import torch
     g = fr.FAISSIndex(128, 'Flat')
